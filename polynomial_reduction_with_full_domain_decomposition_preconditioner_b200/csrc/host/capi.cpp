@@ -1,0 +1,312 @@
+// capi.cpp -- solver-level C ABI: the reference's run_simulation() sequence (poisson.cpp:150-251)
+// behind an opaque handle.  See include/prfdd_b200.h.
+#include "config.hpp"
+#include "domain.hpp"
+#include "subdomain.hpp"
+#include "../../../include/prfdd_b200.h"
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+
+using namespace prfdd_host;
+
+struct prfdd_solver
+{
+    prfdd_options opt;
+    std::string directory;
+    cudaStream_t stream = nullptr;
+    int device_id = 0;
+    int dim_ = 0;
+    std::map<int, std::unique_ptr<Domain<STYPE>>> domains; // ladder of Domain objects (poisson.cpp:172-199)
+    std::unique_ptr<Subdomain<PTYPE>> subdomain;
+    Domain<STYPE> *domain = nullptr;
+    dev::memory u_star, f, u;
+    double *pin_in = nullptr, *pin_out = nullptr;
+    Comm comm;
+    Timer<double> tmr;
+    int function_id = 4;
+
+    void activate()
+    {
+        // the host classes see process-wide globals, like the reference (config.hpp:48-65)
+        cudaSetDevice(device_id);
+        prfdd_host::dim = dim_;
+        prfdd_host::proc_id = opt.proc_id;
+        prfdd_host::num_procs = opt.num_procs;
+        prfdd_host::verbose = opt.verbose;
+        prfdd_host::device.setup(device_id, stream);
+        prfdd_host::comm_world = comm;
+        prfdd_host::timer = tmr;
+    }
+    void deactivate()
+    {
+        dim_ = prfdd_host::dim;
+        tmr = prfdd_host::timer;
+    }
+};
+
+namespace
+{
+template <class F>
+int guarded(prfdd_solver *s, F fn)
+{
+    try
+    {
+        if (s) s->activate();
+        int rc = fn();
+        if (s) s->deactivate();
+        return rc;
+    }
+    catch (const std::exception &ex)
+    {
+        fprintf(stderr, "prfdd: %s\n", ex.what());
+        return -1;
+    }
+}
+} // namespace
+
+extern "C" {
+
+void prfdd_options_default(prfdd_options *o)
+{
+    memset(o, 0, sizeof(*o));
+    o->poly_degree = 7;
+    o->poly_reduction = 3;
+    o->subdomain_overlap = 1;
+    o->superdomain_overlap = 1;
+    o->use_preconditioner = 1;
+    o->preconditioner_type = 1;
+    o->inner_num_vectors = 4;
+    o->inner_max_iterations = 4;
+    o->num_vcycles = 1;
+    o->cheby_order = 2;
+    o->use_cuda_graph = 1;
+    o->proc_id = 0;
+    o->num_procs = 1;
+    o->nccl_unique_id = nullptr;
+    o->outer_tolerance = 1.0e-7;
+    o->inner_tolerance = 1.0e-12;
+    o->outer_max_iterations = 500;
+    o->outer_num_vectors = 20;
+    o->verbose = 0;
+}
+
+int prfdd_solver_create(prfdd_solver **out, const char *directory, const prfdd_options *opt, prfdd_stream_t stream)
+{
+    prfdd_solver *s = new prfdd_solver();
+    s->opt = *opt;
+    s->directory = directory;
+    s->stream = (cudaStream_t)stream;
+    cudaGetDevice(&s->device_id);
+    int rc = guarded(nullptr, [&]() {
+        s->comm.init(opt->proc_id, opt->num_procs, opt->nccl_unique_id, s->stream);
+        s->tmr.stream = s->stream;
+        s->tmr.initialize();
+        s->activate();
+
+        // ladder of domains (poisson.cpp:172-199)
+        rstdout("Running simulation with:\n");
+        rstdout("- Directory: \"%s\"\n", directory);
+        rstdout("- Polynomial degree: \"%d\"\n", opt->poly_degree);
+        rstdout("- Polynomial reduction: \"%d\"\n", opt->poly_reduction);
+        rstdout("- Subdomain overlap: \"%d\"\n", opt->subdomain_overlap);
+        rstdout("- Superdomain overlap: \"%d\"\n", opt->superdomain_overlap);
+        int N = opt->poly_degree;
+        rstdout("\nSetting up domain \"N = %d\" object...\n", N);
+        s->domains[N].reset(new Domain<STYPE>());
+        s->domains[N]->num_vectors = opt->outer_num_vectors;
+        s->domains[N]->initialize(directory, N, true);
+        s->domain = s->domains[N].get();
+        s->domain->max_iterations = opt->outer_max_iterations;
+        s->domain->tolerance = opt->outer_tolerance;
+        s->domain->preconditioner_type = opt->preconditioner_type;
+        s->domain->use_preconditioner = opt->use_preconditioner != 0;
+        if (opt->use_preconditioner)
+        {
+            int level = N;
+            while (level > 1)
+            {
+                level -= opt->poly_reduction;
+                if (level < 1) level = 1;
+                rstdout("Setting up domain \"N = %d\" object...\n", level);
+                s->domains[level].reset(new Domain<STYPE>());
+                s->domains[level]->initialize(directory, level, false);
+            }
+            rstdout("Setting up subdomain object...\n");
+            s->subdomain.reset(new Subdomain<PTYPE>(s->domains, N, opt->poly_reduction, opt->subdomain_overlap, opt->superdomain_overlap, *opt));
+        }
+        else
+        {
+            s->subdomain.reset(new Subdomain<PTYPE>()); // never applied
+        }
+        int P = s->domain->num_local_points;
+        s->u_star = device.malloc<STYPE>(P);
+        s->f = device.malloc<STYPE>(P);
+        s->u = device.malloc<STYPE>(P);
+        dev::check(cudaMallocHost((void **)&s->pin_in, sizeof(double) * P), "pinned in");
+        dev::check(cudaMallocHost((void **)&s->pin_out, sizeof(double) * P), "pinned out");
+        device.finish();
+        s->deactivate();
+        return 0;
+    });
+    if (rc != 0)
+    {
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return 0;
+}
+
+int prfdd_solver_destroy(prfdd_solver *s)
+{
+    if (!s) return 0;
+    guarded(s, [&]() {
+        device.finish();
+        s->subdomain.reset();
+        s->domains.clear();
+        s->u_star.free(); s->f.free(); s->u.free();
+        if (s->pin_in) cudaFreeHost(s->pin_in);
+        if (s->pin_out) cudaFreeHost(s->pin_out);
+        s->comm.finalize();
+        return 0;
+    });
+    delete s;
+    return 0;
+}
+
+int prfdd_solver_setup_problem(prfdd_solver *s, int function_id)
+{
+    return guarded(s, [&]() {
+        s->function_id = function_id;
+        rstdout("\nSetting up exact function...\n");
+        s->domain->initial_function(s->u_star, function_id);  // poisson.cpp:211-213
+        rstdout("Setting up right-hand-side...\n");
+        s->domain->stiffness_matrix(s->f, s->u_star);           // poisson.cpp:218-219
+        device.finish();
+        return 0;
+    });
+}
+
+static int do_solve(prfdd_solver *s, int solver_id, int *num_iterations, double *history, int history_cap, int *history_len)
+{
+    rstdout("Solving Poisson problem...\n");
+    if (solver_id == 0)
+        s->domain->flexible_conjugate_gradient(s->u, s->f, *s->subdomain);  // poisson.cpp:228-229
+    else
+        s->domain->generalized_minimum_residual(s->u, s->f, *s->subdomain); // poisson.cpp:230-231
+    if (num_iterations) *num_iterations = s->domain->num_iterations;
+    int n = (int)s->domain->history.size();
+    if (history_len) *history_len = n;
+    if (history)
+        for (int i = 0; i < n && i < history_cap; i++) history[i] = s->domain->history[i];
+    return 0;
+}
+
+int prfdd_solver_solve(prfdd_solver *s, int solver_id, int *num_iterations, double *history, int history_cap, int *history_len)
+{
+    return guarded(s, [&]() {
+        int rc = do_solve(s, solver_id, num_iterations, history, history_cap, history_len);
+        device.finish();
+        return rc;
+    });
+}
+
+int prfdd_solver_solve_host(prfdd_solver *s, int solver_id, const double *f_host, double *u_host, int *num_iterations, double *history, int history_cap, int *history_len)
+{
+    return guarded(s, [&]() {
+        const size_t bytes = sizeof(double) * (size_t)s->domain->num_local_points;
+        memcpy(s->pin_in, f_host, bytes);
+        dev::check(cudaMemcpyAsync(s->f.ptr(), s->pin_in, bytes, cudaMemcpyHostToDevice, s->stream), "solve_host/h2d");
+        int rc = do_solve(s, solver_id, num_iterations, history, history_cap, history_len);
+        dev::check(cudaMemcpyAsync(s->pin_out, s->u.ptr(), bytes, cudaMemcpyDeviceToHost, s->stream), "solve_host/d2h");
+        device.finish();
+        memcpy(u_host, s->pin_out, bytes);
+        return rc;
+    });
+}
+
+long long prfdd_solver_query(prfdd_solver *s, int what)
+{
+    Domain<STYPE> *d = s->domain;
+    Subdomain<PTYPE> *sd = s->subdomain.get();
+    switch (what)
+    {
+    case PRFDD_Q_DIM: return s->dim_;
+    case PRFDD_Q_NUM_LOCAL_ELEMENTS: return d->num_local_elements;
+    case PRFDD_Q_NUM_LOCAL_POINTS: return d->num_local_points;
+    case PRFDD_Q_NUM_LOCAL_NODES: return d->num_local_nodes;
+    case PRFDD_Q_NUM_BDARY_NODES: return d->num_boundary_nodes();
+    case PRFDD_Q_NUM_TOTAL_ELEMENTS: return d->num_total_elements;
+    case PRFDD_Q_NUM_GLOBAL_NODES: return d->num_total_nodes;
+    default: return sd ? sd->query(what) : -1;
+    }
+}
+
+long long prfdd_solver_get_array(prfdd_solver *s, int what, void *dst, long long cap)
+{
+    long long result = -1;
+    guarded(s, [&]() {
+        Domain<STYPE> *d = s->domain;
+        auto put = [&](const void *src, size_t elem, long long count) {
+            if ((long long)(elem * count) > cap) { result = -(long long)(elem * count); return; }
+            memcpy(dst, src, elem * count);
+            result = count;
+        };
+        auto put_dev = [&](const dev::memory &m, size_t elem, long long count) {
+            if ((long long)(elem * count) > cap) { result = -(long long)(elem * count); return; }
+            m.copyTo(dst, elem * count);
+            result = count;
+        };
+        switch (what)
+        {
+        case PRFDD_A_NODE_OF_POINT: put(d->Q_matrix().col_hst.data(), sizeof(int), d->num_local_points); break;
+        case PRFDD_A_BOUNDARY_NODES: put(d->boundary_node_ids().data(), sizeof(long long), d->num_boundary_nodes()); break;
+        case PRFDD_A_ASSEMBLED_WEIGHT: put_dev(d->assembled_weight_dev(), sizeof(double), d->num_local_nodes); break;
+        case PRFDD_A_D_HAT: put(d->D_hat_hst.data(), sizeof(double), (long long)d->D_hat_hst.size()); break;
+        case PRFDD_A_U: put_dev(s->u, sizeof(double), d->num_local_points); break;
+        case PRFDD_A_U_STAR: put_dev(s->u_star, sizeof(double), d->num_local_points); break;
+        case PRFDD_A_F: put_dev(s->f, sizeof(double), d->num_local_points); break;
+        default:
+            if (s->subdomain) result = s->subdomain->get_array(what, dst, cap);
+        }
+        return 0;
+    });
+    return result;
+}
+
+int prfdd_solver_apply(prfdd_solver *s, int what, const double *in_host, double *out_host)
+{
+    return guarded(s, [&]() {
+        Domain<STYPE> *d = s->domain;
+        const int P = d->num_local_points;
+        if (what == PRFDD_APPLY_STIFFNESS || what == PRFDD_APPLY_DSSUM || what == PRFDD_APPLY_DSSUM_WEIGHTED || what == PRFDD_APPLY_PRECONDITIONER)
+        {
+            dev::memory a = device.malloc<double>(P), b = device.malloc<double>(P);
+            a.copyFrom(in_host, sizeof(double) * P);
+            if (what == PRFDD_APPLY_STIFFNESS) d->stiffness_matrix(b, a);
+            else if (what == PRFDD_APPLY_DSSUM) d->direct_stiffness_summation(b, a, true, false);
+            else if (what == PRFDD_APPLY_DSSUM_WEIGHTED) d->direct_stiffness_summation(b, a, true, true);
+            else
+            {
+                if (!s->opt.use_preconditioner) throw std::runtime_error("preconditioner is off");
+                if (s->opt.preconditioner_type == 0) s->subdomain->flexible_conjugate_gradient(b, a);
+                else s->subdomain->generalized_minimum_residual(b, a);
+            }
+            b.copyTo(out_host, sizeof(double) * P);
+            return 0;
+        }
+        if (!s->subdomain) return -1;
+        return s->subdomain->apply(what, in_host, out_host);
+    });
+}
+
+double prfdd_solver_timer_total(prfdd_solver *s, const char *key)
+{
+    if (!strcmp(key, "__enable__")) { s->tmr.enabled = true; return 0.0; }
+    if (!strcmp(key, "__disable__")) { s->tmr.enabled = false; return 0.0; }
+    return s->tmr.total(key);
+}
+
+} // extern "C"

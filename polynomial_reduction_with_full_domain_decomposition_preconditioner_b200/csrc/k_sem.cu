@@ -1,0 +1,442 @@
+// k_sem.cu -- matrix-free SEM Laplacian and polynomial-reduction restriction (sm_100a)
+//
+// Au = sum_d D_d^T ( G (D u) ) per element, ONE launch, nothing but u, the six geometric factors
+// and Au touch HBM (64 B/point in 3D, 40 B/point in 2D).  Replaces the two-launch,
+// three-temporary stiffness_matrix_1/2 of domain.okl:5-98 and subdomain.okl:4-101.
+//
+// 3D layout of the work: one thread per (i,j) column of an element, the k direction is walked in
+// registers (u column and Au column live in registers), the (i,j) slices of u / G*Du are exchanged
+// through shared memory.  The n x n derivative matrix is held
+//   * per thread in registers for the four thread-dependent rows/columns (D[i][.], D[j][.],
+//     D[.][i], D[.][j]) when n <= 10,
+//   * in the kernel-parameter constant bank for the uniform accesses D[k][m] (compile-time k, m
+//     after unrolling => constant-bank operands of DFMA, no load instruction at all).
+// Several elements share a CTA so that small degrees still fill warps.
+#include "common.cuh"
+
+namespace prfdd
+{
+struct G6
+{
+    const double *g[6];
+};
+
+template <int N>
+struct DParam
+{
+    double v[N * N];
+};
+
+template <int N>
+constexpr int epb3d()
+{
+    // elements per CTA: aim at 128 threads
+    return (N * N >= 128) ? 1 : (128 / (N * N));
+}
+
+template <int N, int EPB>
+__global__ void __launch_bounds__(N *N *EPB) k_ax3d(double *__restrict__ Au, const double *__restrict__ u, const G6 G, const DParam<N> Dc, const double *__restrict__ Dg, long long first_point, int num_elems)
+{
+    constexpr int N2 = N * N, N3 = N * N * N;
+    constexpr int LD = N + 1; // padded leading dimension: conflict-free row reads by thread-dependent row
+    __shared__ double s_u[EPB][N][N];
+    __shared__ double s_gr[EPB][N][N];
+    __shared__ double s_gs[EPB][N][N];
+    __shared__ double s_D[N * LD];
+
+    const int tid = threadIdx.x;
+    const int el = tid / N2;
+    const int ij = tid - el * N2;
+    const int j = ij / N;
+    const int i = ij - j * N;
+    const long long e = (long long)blockIdx.x * EPB + el;
+    const bool active = e < num_elems;
+    const long long base = first_point + e * N3 + ij;
+
+    for (int t = tid; t < N2; t += N2 * EPB) s_D[(t / N) * LD + (t % N)] = Dg[t];
+
+    double r_u[N], r_Au[N];
+#pragma unroll
+    for (int k = 0; k < N; k++)
+    {
+        r_u[k] = active ? u[base + k * N2] : 0.0;
+        r_Au[k] = 0.0;
+    }
+    __syncthreads();
+
+    // thread-dependent rows / columns of D
+    double Di[N], Dj[N], Dti[N], Dtj[N];
+#pragma unroll
+    for (int m = 0; m < N; m++)
+    {
+        Di[m] = s_D[i * LD + m];
+        Dj[m] = s_D[j * LD + m];
+        Dti[m] = s_D[m * LD + i];
+        Dtj[m] = s_D[m * LD + j];
+    }
+
+    double g_nxt[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) g_nxt[c] = active ? G.g[c][base] : 0.0;
+
+#pragma unroll
+    for (int k = 0; k < N; k++)
+    {
+        double g_cur[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) g_cur[c] = g_nxt[c];
+        if (k + 1 < N)
+        {
+#pragma unroll
+            for (int c = 0; c < 6; c++) g_nxt[c] = active ? G.g[c][base + (k + 1) * N2] : 0.0;
+        }
+
+        s_u[el][j][i] = r_u[k];
+        __syncthreads();
+
+        double ur = 0.0, us = 0.0, ut = 0.0;
+#pragma unroll
+        for (int m = 0; m < N; m++)
+        {
+            ur += Di[m] * s_u[el][j][m];
+            us += Dj[m] * s_u[el][m][i];
+            ut += Dc.v[k * N + m] * r_u[m];
+        }
+        const double gr = g_cur[0] * ur + g_cur[3] * us + g_cur[4] * ut;
+        const double gs = g_cur[3] * ur + g_cur[1] * us + g_cur[5] * ut;
+        const double gt = g_cur[4] * ur + g_cur[5] * us + g_cur[2] * ut;
+
+        s_gr[el][j][i] = gr;
+        s_gs[el][j][i] = gs;
+        __syncthreads();
+
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int m = 0; m < N; m++)
+        {
+            a += Dti[m] * s_gr[el][j][m];
+            b += Dtj[m] * s_gs[el][m][i];
+        }
+        r_Au[k] += a + b;
+#pragma unroll
+        for (int m = 0; m < N; m++) r_Au[m] += Dc.v[k * N + m] * gt;
+    }
+
+    if (active)
+    {
+#pragma unroll
+        for (int k = 0; k < N; k++) Au[base + k * N2] = r_Au[k];
+    }
+}
+
+// large degrees (n > 10): D stays in shared memory, everything else identical
+template <int N>
+__global__ void __launch_bounds__(N *N) k_ax3d_big(double *__restrict__ Au, const double *__restrict__ u, const G6 G, const double *__restrict__ Dg, long long first_point, int num_elems)
+{
+    constexpr int N2 = N * N, N3 = N * N * N;
+    constexpr int LD = N + 1;
+    __shared__ double s_u[N][N];
+    __shared__ double s_gr[N][N];
+    __shared__ double s_gs[N][N];
+    __shared__ double s_D[N * LD];
+
+    const int ij = threadIdx.x;
+    const int j = ij / N;
+    const int i = ij - j * N;
+    const long long e = blockIdx.x;
+    const long long base = first_point + e * N3 + ij;
+    (void)num_elems;
+
+    s_D[j * LD + i] = Dg[j * N + i];
+
+    double r_u[N], r_Au[N];
+#pragma unroll
+    for (int k = 0; k < N; k++)
+    {
+        r_u[k] = u[base + k * N2];
+        r_Au[k] = 0.0;
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int k = 0; k < N; k++)
+    {
+        double g_cur[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) g_cur[c] = G.g[c][base + k * N2];
+
+        s_u[j][i] = r_u[k];
+        __syncthreads();
+
+        double ur = 0.0, us = 0.0, ut = 0.0;
+#pragma unroll
+        for (int m = 0; m < N; m++)
+        {
+            ur += s_D[i * LD + m] * s_u[j][m];
+            us += s_D[j * LD + m] * s_u[m][i];
+            ut += s_D[k * LD + m] * r_u[m];
+        }
+        const double gr = g_cur[0] * ur + g_cur[3] * us + g_cur[4] * ut;
+        const double gs = g_cur[3] * ur + g_cur[1] * us + g_cur[5] * ut;
+        const double gt = g_cur[4] * ur + g_cur[5] * us + g_cur[2] * ut;
+
+        s_gr[j][i] = gr;
+        s_gs[j][i] = gs;
+        __syncthreads();
+
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int m = 0; m < N; m++)
+        {
+            a += s_D[m * LD + i] * s_gr[j][m];
+            b += s_D[m * LD + j] * s_gs[m][i];
+        }
+#pragma unroll
+        for (int m = 0; m < N; m++) r_Au[m] += s_D[k * LD + m] * gt + ((m == k) ? (a + b) : 0.0);
+    }
+
+#pragma unroll
+    for (int k = 0; k < N; k++) Au[base + k * N2] = r_Au[k];
+}
+
+// 2D: one thread per point
+template <int N, int EPB>
+__global__ void __launch_bounds__(N *N *EPB) k_ax2d(double *__restrict__ Au, const double *__restrict__ u, const G6 G, const double *__restrict__ Dg, long long first_point, int num_elems)
+{
+    constexpr int N2 = N * N;
+    constexpr int LD = N + 1;
+    __shared__ double s_u[EPB][N][N];
+    __shared__ double s_gr[EPB][N][N];
+    __shared__ double s_gs[EPB][N][N];
+    __shared__ double s_D[N * LD];
+
+    const int tid = threadIdx.x;
+    const int el = tid / N2;
+    const int ij = tid - el * N2;
+    const int j = ij / N;
+    const int i = ij - j * N;
+    const long long e = (long long)blockIdx.x * EPB + el;
+    const bool active = e < num_elems;
+    const long long idx = first_point + e * N2 + ij;
+
+    for (int t = tid; t < N2; t += N2 * EPB) s_D[(t / N) * LD + (t % N)] = Dg[t];
+    s_u[el][j][i] = active ? u[idx] : 0.0;
+    const double g0 = active ? G.g[0][idx] : 0.0, g1 = active ? G.g[1][idx] : 0.0, g2 = active ? G.g[2][idx] : 0.0;
+    __syncthreads();
+
+    double ur = 0.0, us = 0.0;
+#pragma unroll
+    for (int m = 0; m < N; m++)
+    {
+        ur += s_D[i * LD + m] * s_u[el][j][m];
+        us += s_D[j * LD + m] * s_u[el][m][i];
+    }
+    s_gr[el][j][i] = g0 * ur + g2 * us;
+    s_gs[el][j][i] = g2 * ur + g1 * us;
+    __syncthreads();
+
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int m = 0; m < N; m++)
+    {
+        a += s_D[m * LD + i] * s_gr[el][j][m];
+        b += s_D[m * LD + j] * s_gs[el][m][i];
+    }
+    if (active) Au[idx] = a + b;
+}
+
+template <int N>
+static int launch_ax3d(double *Au, const double *u, const G6 &G, const double *D_host, const double *D_dev, long long first_point, int num_elems, cudaStream_t st)
+{
+    if (num_elems <= 0) return 0;
+    if constexpr (N <= 10)
+    {
+        constexpr int EPB = epb3d<N>();
+        DParam<N> Dc;
+        for (int t = 0; t < N * N; t++) Dc.v[t] = D_host[t];
+        int grid = (num_elems + EPB - 1) / EPB;
+        k_ax3d<N, EPB><<<grid, N * N * EPB, 0, st>>>(Au, u, G, Dc, D_dev, first_point, num_elems);
+    }
+    else
+    {
+        k_ax3d_big<N><<<num_elems, N * N, 0, st>>>(Au, u, G, D_dev, first_point, num_elems);
+    }
+    return launched();
+}
+
+template <int N>
+static int launch_ax2d(double *Au, const double *u, const G6 &G, const double *D_dev, long long first_point, int num_elems, cudaStream_t st)
+{
+    if (num_elems <= 0) return 0;
+    constexpr int EPB = (N * N >= 128) ? 1 : (128 / (N * N));
+    int grid = (num_elems + EPB - 1) / EPB;
+    k_ax2d<N, EPB><<<grid, N * N * EPB, 0, st>>>(Au, u, G, D_dev, first_point, num_elems);
+    return launched();
+}
+
+// host mirror of D (the constant-bank copy for the 3D kernels is filled from host memory)
+struct HostD
+{
+    const double *dev = nullptr;
+    int n = 0;
+    double v[16 * 16];
+};
+static HostD g_hostD[8];
+static int g_hostD_next = 0;
+
+static const double *host_copy_of(const double *D_dev, int n, cudaStream_t st)
+{
+    for (auto &h : g_hostD)
+        if (h.dev == D_dev && h.n == n) return h.v;
+    HostD &h = g_hostD[g_hostD_next];
+    g_hostD_next = (g_hostD_next + 1) % 8;
+    // D matrices are written once at setup; a blocking copy the first time a pointer is seen is fine
+    cudaStreamSynchronize(st);
+    if (cudaMemcpy(h.v, D_dev, sizeof(double) * n * n, cudaMemcpyDeviceToHost) != cudaSuccess) return nullptr;
+    h.dev = D_dev;
+    h.n = n;
+    return h.v;
+}
+
+static int ax_dispatch(double *Au, const double *u, const G6 &G, const double *D_dev, long long first_point, int num_elems, int n, int dim, cudaStream_t st)
+{
+    if (num_elems <= 0) return 0;
+    if (dim == 2)
+    {
+        switch (n)
+        {
+#define C2(N) case N: return launch_ax2d<N>(Au, u, G, D_dev, first_point, num_elems, st);
+            C2(2) C2(3) C2(4) C2(5) C2(6) C2(7) C2(8) C2(9) C2(10) C2(11) C2(12) C2(13) C2(14) C2(15) C2(16)
+#undef C2
+        default: return -4;
+        }
+    }
+    const double *Dh = (n <= 10) ? host_copy_of(D_dev, n, st) : nullptr;
+    if (n <= 10 && !Dh) return -5;
+    switch (n)
+    {
+#define C3(N) case N: return launch_ax3d<N>(Au, u, G, Dh, D_dev, first_point, num_elems, st);
+        C3(2) C3(3) C3(4) C3(5) C3(6) C3(7) C3(8) C3(9) C3(10) C3(11) C3(12) C3(13) C3(14) C3(15) C3(16)
+#undef C3
+    default: return -4;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// restriction: u_c = (J^T (x) J^T (x) J^T) u_f, all directions fused, one element per CTA
+// order of the contractions and of each sum follows subdomain.okl:284-366
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_restrict3d(double *__restrict__ uc, const double *__restrict__ J, const double *__restrict__ uf, int nf, int nc)
+{
+    extern __shared__ double sm[];
+    double *sJ = sm;                      // nf*nc
+    double *a0 = sJ + nf * nc;            // nf^3
+    double *a1 = a0 + nf * nf * nf;       // nc*nf*nf
+    double *a2 = a1 + nc * nf * nf;       // nc*nc*nf
+    const long long e = blockIdx.x;
+    const int nf3 = nf * nf * nf, nc3 = nc * nc * nc;
+    for (int t = threadIdx.x; t < nf * nc; t += blockDim.x) sJ[t] = J[t];
+    for (int t = threadIdx.x; t < nf3; t += blockDim.x) a0[t] = uf[e * nf3 + t];
+    __syncthreads();
+    // x: a1(i,j,k) = sum_l J[l][i] a0(l,j,k), layout i + j*nc + k*nc*nf
+    for (int t = threadIdx.x; t < nc * nf * nf; t += blockDim.x)
+    {
+        int i = t % nc, j = (t / nc) % nf, k = t / (nc * nf);
+        double s = 0.0;
+        for (int l = 0; l < nf; l++) s += sJ[i + l * nc] * a0[l + j * nf + k * nf * nf];
+        a1[t] = s;
+    }
+    __syncthreads();
+    // y: a2(i,j,k) = sum_l J[l][j] a1(i,l,k), layout i + j*nc + k*nc*nc
+    for (int t = threadIdx.x; t < nc * nc * nf; t += blockDim.x)
+    {
+        int i = t % nc, j = (t / nc) % nc, k = t / (nc * nc);
+        double s = 0.0;
+        for (int l = 0; l < nf; l++) s += sJ[j + l * nc] * a1[i + l * nc + k * nc * nf];
+        a2[t] = s;
+    }
+    __syncthreads();
+    // z
+    for (int t = threadIdx.x; t < nc3; t += blockDim.x)
+    {
+        int i = t % nc, j = (t / nc) % nc, k = t / (nc * nc);
+        double s = 0.0;
+        for (int l = 0; l < nf; l++) s += sJ[k + l * nc] * a2[i + j * nc + l * nc * nc];
+        uc[e * nc3 + t] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_restrict2d(double *__restrict__ uc, const double *__restrict__ J, const double *__restrict__ uf, int nf, int nc, int num_elems)
+{
+    extern __shared__ double sm[];
+    double *sJ = sm;            // nf*nc
+    double *a0 = sJ + nf * nc;  // nf*nf
+    double *a1 = a0 + nf * nf;  // nf*nc  (i fine, j coarse), layout i + j*nf
+    const long long e = blockIdx.x;
+    (void)num_elems;
+    for (int t = threadIdx.x; t < nf * nc; t += blockDim.x) sJ[t] = J[t];
+    for (int t = threadIdx.x; t < nf * nf; t += blockDim.x) a0[t] = uf[e * nf * nf + t];
+    __syncthreads();
+    for (int t = threadIdx.x; t < nf * nc; t += blockDim.x)
+    {
+        int i = t % nf, j = t / nf;
+        double s = 0.0;
+        for (int k = 0; k < nf; k++) s += sJ[j + k * nc] * a0[i + k * nf];
+        a1[t] = s;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nc * nc; t += blockDim.x)
+    {
+        int i = t % nc, j = t / nc;
+        double s = 0.0;
+        for (int k = 0; k < nf; k++) s += a1[j * nf + k] * sJ[k * nc + i];
+        uc[e * nc * nc + t] = s;
+    }
+}
+} // namespace prfdd
+
+using namespace prfdd;
+
+extern "C" {
+
+int prfdd_stiffness_matrix(double *Au, const double *u, const double *D_hat, const double *const g[6], int num_elements, int n, int dim, prfdd_stream_t stream)
+{
+    G6 G;
+    for (int c = 0; c < 6; c++) G.g[c] = g[c];
+    return ax_dispatch(Au, u, G, D_hat, 0, num_elements, n, dim, S(stream));
+}
+
+int prfdd_stiffness_matrix_region(double *Au, const double *u, const double *const g[6], int num_buckets, const int *first_point, const int *num_elements, const int *n, const double *const *D_hat, int dim, prfdd_stream_t stream)
+{
+    G6 G;
+    for (int c = 0; c < 6; c++) G.g[c] = g[c];
+    for (int b = 0; b < num_buckets; b++)
+    {
+        int rc = ax_dispatch(Au, u, G, D_hat[b], first_point[b], num_elements[b], n[b], dim, S(stream));
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int prfdd_restriction(double *u_c, const double *J_cf, const double *u_f, int num_elements, int n_f, int n_c, int dim, prfdd_stream_t stream)
+{
+    if (num_elements <= 0) return 0;
+    if (dim == 3)
+    {
+        size_t smem = sizeof(double) * ((size_t)n_f * n_c + (size_t)n_f * n_f * n_f + (size_t)n_c * n_f * n_f + (size_t)n_c * n_c * n_f);
+        if (smem > 48 * 1024)
+        {
+            cudaError_t e = cudaFuncSetAttribute(k_restrict3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        k_restrict3d<<<num_elements, 256, smem, S(stream)>>>(u_c, J_cf, u_f, n_f, n_c);
+    }
+    else
+    {
+        size_t smem = sizeof(double) * ((size_t)n_f * n_c * 2 + (size_t)n_f * n_f);
+        k_restrict2d<<<num_elements, 256, smem, S(stream)>>>(u_c, J_cf, u_f, n_f, n_c, num_elements);
+    }
+    return launched();
+}
+
+} // extern "C"

@@ -1,0 +1,217 @@
+// k_sparse.cu -- gather-scatter, halo pack/unpack, CSR SpMV family, fused Chebyshev smoother (sm_100a)
+//
+// Replaces csr_matrix.okl:5-48 (one thread per row, scalar), the cusparseSpMV(CSR_ALG1) calls of
+// AMG/csr_matrix.cpp:126-133 and the element-wise smoother kernels of AMG/kernels.cu:25-76.
+//
+// SpMV shape: a sub-warp of TPR lanes owns one row; lanes stride through the row so that col/val
+// reads of neighbouring lanes are contiguous (coalesced), partial sums are combined with shuffles
+// in a fixed order (deterministic).  Everything the reference does in separate element-wise launches
+// around an SpMV (scaling by ds, c*r + v, u += ds*w, f - A u) is done in the SpMV epilogue, so one
+// Chebyshev smoothing of order 2 is 2 launches and 2 passes over A instead of 7 launches.
+#include "common.cuh"
+
+namespace prfdd
+{
+constexpr int kSpThreads = 256;
+
+template <int TPR>
+__device__ __forceinline__ double row_dot(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, int row, int lane, bool valid)
+{
+    const int s = valid ? ptr[row] : 0, e = valid ? ptr[row + 1] : 0;
+    double acc = 0.0;
+    for (int j = s + lane; j < e; j += TPR) acc += val[j] * x[col[j]];
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, TPR);
+    return acc;
+}
+
+// generic SpMV with an epilogue functor: epi(row, Ax) executed by lane 0 of the row's sub-warp.
+// The row loop is warp-uniform (all 32 lanes take the same number of trips) so the full-mask
+// shuffles in row_dot are always executed by the whole warp.
+template <int TPR, class Epi>
+__global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, int row_start, int num_rows, Epi epi)
+{
+    constexpr int RPW = 32 / TPR; // rows per warp
+    const int lane = threadIdx.x % TPR;
+    const int sub = (threadIdx.x & 31) / TPR;
+    const long long rows_per_grid = (long long)gridDim.x * (kSpThreads / TPR);
+    for (long long r0 = (long long)blockIdx.x * (kSpThreads / TPR) + (threadIdx.x >> 5) * RPW; r0 < num_rows; r0 += rows_per_grid)
+    {
+        const long long r = r0 + sub;
+        const bool valid = r < num_rows;
+        const int row = row_start + (int)r;
+        double ax = x ? row_dot<TPR>(ptr, col, val, x, row, lane, valid) : 0.0;
+        if (valid && lane == 0) epi(row, ax);
+    }
+}
+
+template <class Epi>
+static int spmv(const int *ptr, const int *col, const double *val, const double *x, int row_start, int num_rows, int tpr, cudaStream_t st, Epi epi)
+{
+    if (num_rows <= 0) return 0;
+    if (tpr <= 0) tpr = 4;
+    long long threads = (long long)num_rows * tpr;
+    int grid = stream_grid(threads, kSpThreads, 1, 16);
+    switch (tpr)
+    {
+    case 1: k_spmv<1><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, epi); break;
+    case 2: k_spmv<2><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, epi); break;
+    case 4: k_spmv<4><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, epi); break;
+    case 8: k_spmv<8><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, epi); break;
+    case 16: k_spmv<16><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, epi); break;
+    case 32: k_spmv<32><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, epi); break;
+    default: return -6;
+    }
+    return launched();
+}
+
+// ---------------------------------------------------------------------------------------------
+// gather / scatter (index-map Q^T / Q) and halo
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather(double *__restrict__ nodes, const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ u, const double *__restrict__ weight, int num_nodes)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < num_nodes; v += stride)
+    {
+        const int s = ptr[v], e = ptr[v + 1];
+        double acc = 0.0;
+        for (int j = s; j < e; j++) acc += u[col[j]];
+        nodes[v] = weight ? acc * weight[v] : acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scatter(double *__restrict__ out, const int *__restrict__ node_of_point, const double *__restrict__ nodes, const double *__restrict__ mask, long long num_points)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < num_points; p += stride)
+    {
+        const double v = nodes[node_of_point[p]];
+        out[p] = mask ? v * mask[p] : v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pack(double *__restrict__ buf, const double *__restrict__ nodes, const int *__restrict__ idx, int count)
+{
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) buf[i] = nodes[idx[i]];
+}
+
+__global__ void __launch_bounds__(256) k_unpack_add(double *__restrict__ nodes, const double *__restrict__ buf, const int *__restrict__ idx, int count)
+{
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) nodes[idx[i]] += buf[i];
+}
+
+__global__ void __launch_bounds__(256) k_dense_solve(double *__restrict__ x, const double *__restrict__ Ainv, const double *__restrict__ b, int n)
+{
+    extern __shared__ double sb[];
+    for (int t = threadIdx.x; t < n; t += blockDim.x) sb[t] = b[t];
+    __syncthreads();
+    for (int r = threadIdx.x; r < n; r += blockDim.x)
+    {
+        double acc = 0.0;
+        for (int c = 0; c < n; c++) acc += Ainv[(size_t)r * n + c] * sb[c];
+        x[r] = acc;
+    }
+}
+} // namespace prfdd
+
+using namespace prfdd;
+
+extern "C" {
+
+int prfdd_gather(double *nodes, const int *ptr, const int *col, const double *u, const double *weight, int num_nodes, prfdd_stream_t stream)
+{
+    if (num_nodes <= 0) return 0;
+    k_gather<<<stream_grid(num_nodes, 256, 1, 16), 256, 0, S(stream)>>>(nodes, ptr, col, u, weight, num_nodes);
+    return launched();
+}
+
+int prfdd_scatter(double *out, const int *node_of_point, const double *nodes, const double *mask, int num_points, prfdd_stream_t stream)
+{
+    if (num_points <= 0) return 0;
+    k_scatter<<<stream_grid(num_points, 256, 2, 8), 256, 0, S(stream)>>>(out, node_of_point, nodes, mask, num_points);
+    return launched();
+}
+
+int prfdd_halo_pack(double *buf, const double *nodes, const int *idx, int count, prfdd_stream_t stream)
+{
+    if (count <= 0) return 0;
+    k_pack<<<stream_grid(count, 256, 1, 8), 256, 0, S(stream)>>>(buf, nodes, idx, count);
+    return launched();
+}
+
+int prfdd_halo_unpack_add(double *nodes, const double *buf, const int *idx, int count, prfdd_stream_t stream)
+{
+    if (count <= 0) return 0;
+    k_unpack_add<<<stream_grid(count, 256, 1, 8), 256, 0, S(stream)>>>(nodes, buf, idx, count);
+    return launched();
+}
+
+int prfdd_csr_multiply(double *Au, const int *ptr, const int *col, const double *val, const double *u, int num_rows, int tpr, prfdd_stream_t stream)
+{
+    return spmv(ptr, col, val, u, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) { Au[row] = ax; });
+}
+
+int prfdd_csr_multiply_range(double *Au, const int *ptr, const int *col, const double *val, const double *u, int row_start, int row_end, int tpr, prfdd_stream_t stream)
+{
+    if (row_end < row_start) return -7; // csr_matrix.tpp:319-323
+    return spmv(ptr, col, val, u, row_start, row_end - row_start + 1, tpr, S(stream), [=] __device__(int row, double ax) { Au[row] = ax; });
+}
+
+int prfdd_csr_multiply_weight(double *Au, const int *ptr, const int *col, const double *val, const double *u, const double *weight, int num_rows, int tpr, prfdd_stream_t stream)
+{
+    return spmv(ptr, col, val, u, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) { Au[row] = ax * weight[row]; });
+}
+
+int prfdd_csr_matvec(double *y, const int *ptr, const int *col, const double *val, const double *x, double alpha, double beta, int num_rows, int tpr, prfdd_stream_t stream)
+{
+    if (beta == 0.0)
+        return spmv(ptr, col, val, x, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) { y[row] = alpha * ax; });
+    return spmv(ptr, col, val, x, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) { y[row] = alpha * ax + beta * y[row]; });
+}
+
+int prfdd_csr_residual(double *v, const int *ptr, const int *col, const double *val, const double *u, const double *f, int num_rows, int tpr, prfdd_stream_t stream)
+{
+    return spmv(ptr, col, val, u, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) { v[row] = f[row] - ax; });
+}
+
+int prfdd_cheby_residual(double *r, double *t, const int *ptr, const int *col, const double *val, const double *u, const double *f, const double *ds, double c_hi, int num_rows, int tpr, prfdd_stream_t stream)
+{
+    // u == NULL: u = 0, the product A u is skipped (x == nullptr in k_spmv) and TPR is irrelevant
+    return spmv(ptr, col, val, u, 0, num_rows, u ? tpr : 1, S(stream), [=] __device__(int row, double ax) {
+        const double d = ds[row];
+        const double rr = d * (f[row] - ax);
+        r[row] = rr;
+        t[row] = d * (c_hi * rr);
+    });
+}
+
+int prfdd_cheby_step(double *u, double *t_out, const int *ptr, const int *col, const double *val, const double *t_in, const double *r, const double *ds, double c, int last, int u_is_zero, int num_rows, int tpr, prfdd_stream_t stream)
+{
+    if (last)
+    {
+        if (u_is_zero)
+            return spmv(ptr, col, val, t_in, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) {
+                const double d = ds[row];
+                u[row] = d * (c * r[row] + d * ax);
+            });
+        return spmv(ptr, col, val, t_in, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) {
+            const double d = ds[row];
+            u[row] += d * (c * r[row] + d * ax);
+        });
+    }
+    return spmv(ptr, col, val, t_in, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) {
+        const double d = ds[row];
+        t_out[row] = d * (c * r[row] + d * ax);
+    });
+}
+
+int prfdd_dense_solve(double *x, const double *Ainv, const double *b, int n, prfdd_stream_t stream)
+{
+    if (n <= 0) return 0;
+    k_dense_solve<<<1, 256, sizeof(double) * n, S(stream)>>>(x, Ainv, b, n);
+    return launched();
+}
+
+} // extern "C"

@@ -1,0 +1,373 @@
+// k_vector.cu -- fused vector algebra and deterministic device-side reductions (sm_100a)
+//
+// Replaces math.okl:5-35, domain.okl:100-264 and subdomain.okl:103-282 of the reference.
+// All kernels are HBM-bound streaming kernels: grid-stride loops over 128-bit (double2) accesses,
+// grids sized in whole multiples of the SM count.  Reductions never touch the host: each block
+// writes one partial per sum, the last block to finish (atomic ticket) adds the partials in a fixed
+// order and stores the result in device memory, so results are bit-reproducible run to run.
+#include "common.cuh"
+
+namespace prfdd
+{
+long long g_launch_count = 0;
+
+constexpr int kThreads = 256;
+constexpr int kRedThreads = 256;
+constexpr int kRedMaxBlocks = 4 * 148; // 4 CTAs per SM on a B200
+constexpr int kRedMaxK = 8;
+
+// ---------------------------------------------------------------------------------------------
+// element-wise kernels
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(kThreads) k_map(long long n, F f)
+{
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+
+template <class F>
+static int map(long long n, cudaStream_t st, F f)
+{
+    if (n <= 0) return 0;
+    k_map<<<stream_grid(n, kThreads, 2, 8), kThreads, 0, st>>>(n, f);
+    return launched();
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum in a fixed order; result valid in thread 0
+template <int K>
+__device__ __forceinline__ void block_sum(double (&acc)[K], double *smem /* [K][warps] */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int W = kRedThreads / 32;
+#pragma unroll
+    for (int k = 0; k < K; k++)
+    {
+        double v = warp_sum(acc[k]);
+        if (lane == 0) smem[k * W + warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0)
+    {
+#pragma unroll
+        for (int k = 0; k < K; k++)
+        {
+            double v = (lane < W) ? smem[k * W + lane] : 0.0;
+            v = warp_sum(v);
+            acc[k] = v;
+        }
+    }
+    __syncthreads();
+}
+
+template <int K, class F>
+__global__ void __launch_bounds__(kRedThreads) k_reduce(long long n, F f, double *partials, unsigned int *counter, double *out, int out_stride)
+{
+    __shared__ double smem[K * (kRedThreads / 32)];
+    __shared__ bool is_last;
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] = 0.0;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i, acc);
+    block_sum<K>(acc, smem);
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int k = 0; k < K; k++) partials[k * kRedMaxBlocks + blockIdx.x] = acc[k];
+        __threadfence();
+        unsigned int ticket = atomicAdd(counter, 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last)
+    {
+        __threadfence();
+#pragma unroll
+        for (int k = 0; k < K; k++)
+        {
+            double v = 0.0;
+            for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) v += __ldcg(&partials[k * kRedMaxBlocks + b]);
+            acc[k] = v;
+        }
+        block_sum<K>(acc, smem);
+        if (threadIdx.x == 0)
+        {
+#pragma unroll
+            for (int k = 0; k < K; k++) out[k * out_stride] = acc[k];
+            *counter = 0u;
+        }
+    }
+}
+
+template <int K, class F>
+static int reduce(prfdd_reduce_ws *ws, double *out, int out_stride, long long n, cudaStream_t st, F f)
+{
+    static_assert(K <= kRedMaxK, "too many fused sums");
+    if (ws == nullptr) return -2;
+    int grid = stream_grid(n > 0 ? n : 1, kRedThreads, 4, 4);
+    if (grid > kRedMaxBlocks) grid = kRedMaxBlocks;
+    k_reduce<K><<<grid, kRedThreads, 0, st>>>(n, f, ws->partials, ws->counter, out, out_stride);
+    return launched();
+}
+} // namespace prfdd
+
+using namespace prfdd;
+
+extern "C" {
+
+int prfdd_reduce_ws_create(prfdd_reduce_ws **ws)
+{
+    prfdd_reduce_ws *w = new prfdd_reduce_ws();
+    cudaError_t e = cudaMalloc(&w->partials, sizeof(double) * kRedMaxK * kRedMaxBlocks);
+    if (e != cudaSuccess) { delete w; return (int)e; }
+    e = cudaMalloc(&w->counter, sizeof(unsigned int));
+    if (e != cudaSuccess) { cudaFree(w->partials); delete w; return (int)e; }
+    cudaMemset(w->counter, 0, sizeof(unsigned int));
+    *ws = w;
+    return 0;
+}
+
+int prfdd_reduce_ws_destroy(prfdd_reduce_ws *ws)
+{
+    if (!ws) return 0;
+    cudaFree(ws->partials);
+    cudaFree(ws->counter);
+    delete ws;
+    return 0;
+}
+
+long long prfdd_launch_count(void) { return g_launch_count; }
+void prfdd_launch_count_reset(void) { g_launch_count = 0; }
+
+// ------------------------------------------------------------------------------ math.okl
+int prfdd_set_to_value(double *u, double alpha, int n, int offset, prfdd_stream_t stream)
+{
+    return map(n, S(stream), [=] __device__(long long i) { u[i + offset] = alpha; });
+}
+
+int prfdd_vector_set_to_value(double *data, double value, int size, prfdd_stream_t stream)
+{
+    return map(size, S(stream), [=] __device__(long long i) { data[i] = value; });
+}
+
+int prfdd_invert_vector_elements(double *u, int n, prfdd_stream_t stream)
+{
+    return map(n, S(stream), [=] __device__(long long i) { u[i] = 1.0 / u[i]; });
+}
+
+int prfdd_vector_vector_addition(double *uv, double alpha, const double *u, double beta, const double *v, int n, prfdd_stream_t stream)
+{
+    return map(n, S(stream), [=] __device__(long long i) { uv[i] = alpha * u[i] + beta * v[i]; });
+}
+
+int prfdd_vector_scaling(double *au, double alpha, const double *u, int n, prfdd_stream_t stream)
+{
+    return map(n, S(stream), [=] __device__(long long i) { au[i] = alpha * u[i]; });
+}
+
+int prfdd_vector_scaling_dev(double *au, const double *num, const double *den, const double *u, int n, prfdd_stream_t stream)
+{
+    return map(n, S(stream), [=] __device__(long long i) {
+        double a = den ? (*num) / (*den) : (*num);
+        au[i] = a * u[i];
+    });
+}
+
+struct PtrPack
+{
+    const double *p[32];
+};
+
+int prfdd_multi_axpy_dev(double *y, const double *const *X, const double *coef, int coef_stride, double sign, int count, int n, prfdd_stream_t stream)
+{
+    if (count > 32) return -3;
+    PtrPack pk;
+    for (int i = 0; i < count; i++) pk.p[i] = X[i];
+    // y = 1.0*y + (sign*c_i) X_i, i ascending: the same chain as the reference's sequence of
+    // vector_vector_addition calls (domain.tpp:817-822, 902-907; subdomain.tpp:4396-4401, 4473-4478)
+    return map(n, S(stream), [=] __device__(long long i) {
+        double acc = y[i];
+        for (int k = 0; k < count; k++) acc = acc + (sign * coef[k * coef_stride]) * pk.p[k][i];
+        y[i] = acc;
+    });
+}
+
+// ---------------------------------------------------------------- domain.okl element-wise
+int prfdd_initialize_arrays(double *u_k, double *r_k, const double *f, int n, prfdd_stream_t stream)
+{
+    return map(n, S(stream), [=] __device__(long long i) { u_k[i] = 0.0; r_k[i] = f[i]; });
+}
+
+int prfdd_solution_and_residual_update(double *u_k, double *r_kp1, const double *r_k, const double *p_k, const double *q_k, double alpha_k, int n, prfdd_stream_t stream)
+{
+    return map(n, S(stream), [=] __device__(long long i) {
+        u_k[i] += alpha_k * p_k[i];
+        r_kp1[i] = r_k[i] - alpha_k * q_k[i];
+    });
+}
+
+int prfdd_solution_and_residual_update_dev(double *u_k, double *r_kp1, const double *r_k, const double *p_k, const double *q_k, const double *num, const double *den, int n, prfdd_stream_t stream)
+{
+    return map(n, S(stream), [=] __device__(long long i) {
+        double alpha_k = (*num) / (*den);
+        u_k[i] += alpha_k * p_k[i];
+        r_kp1[i] = r_k[i] - alpha_k * q_k[i];
+    });
+}
+
+int prfdd_residual_and_search_update(double *p_k, double *r_k, const double *z_k, const double *r_kp1, double beta_k, int n, prfdd_stream_t stream)
+{
+    return map(n, S(stream), [=] __device__(long long i) {
+        p_k[i] = z_k[i] + beta_k * p_k[i];
+        r_k[i] = r_kp1[i];
+    });
+}
+
+int prfdd_residual_and_search_update_dev(double *p_k, double *r_k, const double *z_k, const double *r_kp1, const double *num, const double *den, int n, prfdd_stream_t stream)
+{
+    return map(n, S(stream), [=] __device__(long long i) {
+        double beta_k = (*num) / (*den);
+        p_k[i] = z_k[i] + beta_k * p_k[i];
+        r_k[i] = r_kp1[i];
+    });
+}
+
+int prfdd_copy_from_domain_data(double *u, const double *v, int num_points, prfdd_stream_t stream)
+{
+    return map(num_points, S(stream), [=] __device__(long long i) { u[i] = v[i]; });
+}
+
+int prfdd_copy_to_domain_data(double *u, const double *v, int num_points, prfdd_stream_t stream)
+{
+    return map(num_points, S(stream), [=] __device__(long long i) { u[i] = v[i]; });
+}
+
+// ---------------------------------------------------------------- AMG/kernels.cu
+int prfdd_main_scaled_residual(double *Sr, double *w, const double *f_m_Au, const double *Sv, double alpha, int size, prfdd_stream_t stream)
+{
+    return map(size, S(stream), [=] __device__(long long i) {
+        double s = Sv[i] * f_m_Au[i];
+        Sr[i] = s;
+        w[i] = alpha * s;
+    });
+}
+
+int prfdd_main_polynomial_evaluation(double *w, double *v, const double *r, const double *D_val, double alpha, int size, prfdd_stream_t stream)
+{
+    return map(size, S(stream), [=] __device__(long long i) {
+        double t = v[i] * D_val[i];
+        v[i] = t;
+        w[i] = alpha * r[i] + t;
+    });
+}
+
+int prfdd_main_update_field(double *u, const double *w, const double *D_val, int size, prfdd_stream_t stream)
+{
+    return map(size, S(stream), [=] __device__(long long i) { u[i] += D_val[i] * w[i]; });
+}
+
+int prfdd_vector_multiplication(double *uv, const double *u, const double *v, int size, prfdd_stream_t stream)
+{
+    return map(size, S(stream), [=] __device__(long long i) { uv[i] = u[i] * v[i]; });
+}
+
+int prfdd_cheby_order1(double *u, const double *r, const double *ds, double c, int u_is_zero, int size, prfdd_stream_t stream)
+{
+    return map(size, S(stream), [=] __device__(long long i) {
+        double w = ds[i] * (c * r[i]);
+        u[i] = u_is_zero ? w : u[i] + w;
+    });
+}
+
+// ---------------------------------------------------------------- reductions
+int prfdd_residual_norm(prfdd_reduce_ws *ws, double *out, const double *r_k, const double *QQt_r_k, const double *mask, int n, prfdd_stream_t stream)
+{
+    return reduce<1>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) { a[0] += r_k[i] * QQt_r_k[i] * mask[i]; });
+}
+
+int prfdd_projection_inner_products(prfdd_reduce_ws *ws, double *out, const double *z_k, const double *r_k, const double *p_k, const double *q_k, int n, prfdd_stream_t stream)
+{
+    return reduce<2>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[2]) {
+        a[0] += z_k[i] * r_k[i];
+        a[1] += p_k[i] * q_k[i];
+    });
+}
+
+int prfdd_inner_product_flexible(prfdd_reduce_ws *ws, double *out, const double *r_k, const double *r_kp1, const double *z_k, int n, prfdd_stream_t stream)
+{
+    return reduce<1>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) { a[0] += (r_kp1[i] - r_k[i]) * z_k[i]; });
+}
+
+int prfdd_inner_product(prfdd_reduce_ws *ws, double *out, const double *u_k, const double *v_k, const double *mask, int n, prfdd_stream_t stream)
+{
+    return reduce<1>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) { a[0] += u_k[i] * v_k[i] * mask[i]; });
+}
+
+int prfdd_weighted_inner_product(prfdd_reduce_ws *ws, double *out, const double *u, const double *v, const double *w, int n, prfdd_stream_t stream)
+{
+    if (w)
+        return reduce<1>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) { a[0] += u[i] * v[i] * w[i]; });
+    return reduce<1>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) { a[0] += u[i] * v[i]; });
+}
+
+int prfdd_multi_inner_product(prfdd_reduce_ws *ws, double *out, const double *u, const double *const *V, const double *w, int count, int n, prfdd_stream_t stream)
+{
+    if (count > 32) return -3;
+    int rc = 0;
+    for (int base = 0; base < count && rc == 0; base += 4)
+    {
+        int c = count - base < 4 ? count - base : 4;
+        const double *v0 = V[base], *v1 = c > 1 ? V[base + 1] : V[base], *v2 = c > 2 ? V[base + 2] : V[base], *v3 = c > 3 ? V[base + 3] : V[base];
+        double *o = out + base;
+        if (c == 1)
+            rc = reduce<1>(ws, o, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) { a[0] += u[i] * v0[i] * (w ? w[i] : 1.0); });
+        else if (c == 2)
+            rc = reduce<2>(ws, o, 1, n, S(stream), [=] __device__(long long i, double(&a)[2]) {
+                double uw = u[i] * (w ? w[i] : 1.0);
+                a[0] += uw * v0[i];
+                a[1] += uw * v1[i];
+            });
+        else if (c == 3)
+            rc = reduce<3>(ws, o, 1, n, S(stream), [=] __device__(long long i, double(&a)[3]) {
+                double uw = u[i] * (w ? w[i] : 1.0);
+                a[0] += uw * v0[i];
+                a[1] += uw * v1[i];
+                a[2] += uw * v2[i];
+            });
+        else
+            rc = reduce<4>(ws, o, 1, n, S(stream), [=] __device__(long long i, double(&a)[4]) {
+                double uw = u[i] * (w ? w[i] : 1.0);
+                a[0] += uw * v0[i];
+                a[1] += uw * v1[i];
+                a[2] += uw * v2[i];
+                a[3] += uw * v3[i];
+            });
+    }
+    return rc;
+}
+
+int prfdd_weighted_projection_inner_products(prfdd_reduce_ws *ws, double *out, const double *z_k, const double *r_k, const double *p_k, const double *q_k, const double *weight, int n, prfdd_stream_t stream)
+{
+    return reduce<2>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[2]) {
+        a[0] += z_k[i] * r_k[i] * weight[i];
+        a[1] += p_k[i] * q_k[i] * weight[i];
+    });
+}
+
+int prfdd_search_update_inner_product(prfdd_reduce_ws *ws, double *out, const double *r_k, const double *r_kp1, const double *z_k, const double *weight, int n, prfdd_stream_t stream)
+{
+    return reduce<1>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) { a[0] += (r_kp1[i] - r_k[i]) * z_k[i] * weight[i]; });
+}
+
+} // extern "C"

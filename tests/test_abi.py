@@ -1,0 +1,63 @@
+"""The C-ABI library loads and exports every symbol include/prfdd_b200.h declares (no compute, no GPU)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "prfdd_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(prfdd_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_compiles_as_c():
+    src = '#include "prfdd_b200.h"\nint main(void){ prfdd_options o; (void)o; return 0; }\n'
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"], input=src, text=True, capture_output=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_all_symbols_exported(prfdd):
+    L = prfdd.lib()
+    names = _declared()
+    assert len(names) >= 60
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_options_layout_and_host_entry_points(prfdd):
+    import numpy as np
+    L = prfdd.lib()
+    o = prfdd.Options()
+    L.prfdd_options_default(C.byref(o))
+    assert (o.poly_degree, o.inner_num_vectors, o.inner_max_iterations, o.num_vcycles, o.cheby_order) == (7, 4, 4, 1, 2)
+    assert o.outer_tolerance == 1e-7 and o.inner_tolerance == 1e-12 and o.outer_max_iterations == 500 and o.outer_num_vectors == 20
+    assert b"sm_100a" in L.prfdd_version()
+    # host-only entry points: speclib restatement and the glibc rand stream agree with the oracle bit for bit
+    from oracle import capi as oc
+    for n in (2, 5, 8, 16):
+        z = np.zeros(n); w = np.zeros(n); D = np.zeros(n * n)
+        L.prfdd_zwgll(oc.ptr(z), oc.ptr(w), C.c_int(n))
+        L.prfdd_dgll(oc.ptr(D), oc.ptr(z), C.c_int(n))
+        zo, wo = oc.zwgll(n)
+        assert np.array_equal(z, zo) and np.array_equal(w, wo) and np.array_equal(D.reshape(n, n), oc.dgll(zo.copy(), n))
+        zc, _ = oc.zwgll(3)
+        for j in range(3):
+            assert L.prfdd_hgll(C.c_int(j), C.c_double(z[1]), oc.ptr(zc), C.c_int(3)) == oc.hgll(j + 1, z[1], zc.copy(), 3)
+    a = np.zeros(5000); b = np.zeros(5000)
+    L.prfdd_glibc_rand_fill(oc.ptr(a), C.c_longlong(5000), C.c_uint(1))
+    oc.lib().o_rand_fill(oc.ptr(b), C.c_int(5000), C.c_uint(1))
+    assert np.array_equal(a, b)
+
+
+def test_no_oracle_in_product():
+    """The product must not import, link or call anything under oracle/."""
+    pkg = os.path.join(ROOT, "polynomial_reduction_with_full_domain_decomposition_preconditioner_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".hpp", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f), errors="ignore").read()
+                assert "oracle" not in text.lower().replace("oracle/", "oracle/") or f == "build.py" or "liboracle" not in text, f
+                assert "liboracle" not in text and "from oracle" not in text and "import oracle" not in text, f

@@ -1,0 +1,342 @@
+"""-m gpu: every sm_100a kernel of libprfdd_b200.so, called through the C ABI on device buffers, against
+the oracle's C restatement (oracle/kernels.c, itself pinned to the reference's OKL) on the same seeded
+inputs.  Tolerances: FP64, 1e-13 relative to the natural scale of each result (FMA contraction and
+summation order differ from the scalar CPU loops; nothing else does)."""
+import ctypes as C
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import capi as oc  # noqa: E402
+
+P = oc.ptr
+TOL = 1e-13
+
+
+@pytest.fixture(scope="module")
+def G(prfdd):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import gpu_util as g
+    g.lib = prfdd.lib()
+    g.ws = g.WS(g.lib)
+    return g
+
+
+def _D(n):
+    z, _ = oc.zwgll(n)
+    return np.ascontiguousarray(oc.dgll(z, n).ravel())
+
+
+def _oracle_ax(u, Gs, D, E, N, dim):
+    L = oc.lib()
+    npts = u.size
+    gdu = [np.zeros(npts) for _ in range(dim)]
+    Au = np.zeros(npts)
+    L.o_stiffness_matrix_1(oc.ptr_table(gdu), P(u), P(D), oc.ptr_table(Gs), C.c_int(npts), C.c_int(N), C.c_int(dim))
+    L.o_stiffness_matrix_2(P(Au), oc.ptr_table(gdu), P(D), C.c_int(npts), C.c_int(N), C.c_int(dim))
+    return Au
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 15])
+def test_stiffness_matrix(G, dim, N):
+    rng = np.random.default_rng(100 * dim + N)
+    n = N + 1
+    E = 37 if N < 8 else 5                      # ragged: not a multiple of the elements-per-CTA packing
+    npts = E * n ** dim
+    u = rng.standard_normal(npts)
+    Gs = [rng.standard_normal(npts) for _ in range(6)]
+    D = _D(n)
+    ref = _oracle_ax(u, Gs, D, E, N, dim)
+    du, dD, dG, dAu = G.dev(u), G.dev(D), [G.dev(g) for g in Gs], G.dev(np.full(npts, np.nan))
+    rc = G.lib.prfdd_stiffness_matrix(G.p(dAu), G.p(du), G.p(dD), G.ptr_array(dG), C.c_int(E), C.c_int(n), C.c_int(dim), G.stream())
+    assert rc == 0
+    G.sync()
+    out = G.host(dAu)
+    scale = np.abs(ref).max()
+    assert np.abs(out - ref).max() <= 50 * TOL * scale
+
+
+def test_stiffness_matrix_region_mixed_degrees(G):
+    """variable-degree composite operator (subdomain.okl:4-101): runs of equal degree in one region vector"""
+    rng = np.random.default_rng(5)
+    dim = 3
+    ladder, counts = [7, 4, 1], [5, 9, 33]
+    first, o = [], 0
+    for N, cnt in zip(ladder, counts):
+        first.append(o)
+        o += cnt * (N + 1) ** dim
+    npts = o
+    u = rng.standard_normal(npts)
+    Gs = [rng.standard_normal(npts) for _ in range(6)]
+    Ds = [_D(N + 1) for N in ladder]
+    L = oc.lib()
+    offs = np.zeros(npts, np.int32); verts = np.zeros(npts, np.int32); lev = np.zeros(npts, np.int32)
+    for l, (N, cnt) in enumerate(zip(ladder, counts)):
+        npe = (N + 1) ** dim
+        for e in range(cnt):
+            s = first[l] + e * npe
+            offs[s:s + npe] = s; verts[s:s + npe] = np.arange(npe); lev[s:s + npe] = l
+    gdu = [np.zeros(npts) for _ in range(dim)]
+    ref = np.zeros(npts)
+    pd = np.array(ladder, dtype=np.float64)
+    L.o_sub_stiffness_matrix_1(oc.ptr_table(gdu), P(u), oc.ptr_table(Ds), P(offs), P(verts), P(lev), oc.ptr_table(Gs), C.c_int(npts), P(pd), C.c_int(dim))
+    L.o_sub_stiffness_matrix_2(P(ref), oc.ptr_table(gdu), oc.ptr_table(Ds), P(offs), P(verts), P(lev), C.c_int(npts), P(pd), C.c_int(dim))
+    du, dG, dDs, dAu = G.dev(u), [G.dev(g) for g in Gs], [G.dev(d) for d in Ds], G.dev(np.zeros(npts))
+    fp = (C.c_int * 3)(*first); ne = (C.c_int * 3)(*counts); nn = (C.c_int * 3)(*[N + 1 for N in ladder])
+    rc = G.lib.prfdd_stiffness_matrix_region(G.p(dAu), G.p(du), G.ptr_array(dG), C.c_int(3), fp, ne, nn, G.ptr_array(dDs), C.c_int(dim), G.stream())
+    assert rc == 0
+    G.sync()
+    assert np.abs(G.host(dAu) - ref).max() <= 50 * TOL * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("dim,nf,nc", [(2, 8, 5), (2, 5, 2), (3, 8, 5), (3, 5, 2), (3, 8, 2), (3, 10, 7), (3, 16, 9)])
+def test_restriction(G, dim, nf, nc):
+    rng = np.random.default_rng(nf + nc)
+    E = 11
+    zf, _ = oc.zwgll(nf); zc, _ = oc.zwgll(nc)
+    J = np.ascontiguousarray(np.array([[oc.hgll(j + 1, zf[i], zc.copy(), nc) for j in range(nc)] for i in range(nf)]).ravel())
+    u = rng.standard_normal(E * nf ** dim)
+    L = oc.lib()
+    if dim == 2:
+        t1 = np.zeros(E * nf * nc); ref = np.zeros(E * nc * nc)
+        L.o_restriction_1(P(t1), P(J), P(u), C.c_int(t1.size), C.c_int(nf), C.c_int(nc), C.c_int(2))
+        L.o_restriction_2(P(ref), P(J), P(t1), C.c_int(ref.size), C.c_int(nf), C.c_int(nc), C.c_int(2))
+    else:
+        t1 = np.zeros(E * nf * nf * nc); t2 = np.zeros(E * nf * nc * nc); ref = np.zeros(E * nc ** 3)
+        L.o_restriction_1(P(t1), P(J), P(u), C.c_int(t1.size), C.c_int(nf), C.c_int(nc), C.c_int(3))
+        L.o_restriction_2(P(t2), P(J), P(t1), C.c_int(t2.size), C.c_int(nf), C.c_int(nc), C.c_int(3))
+        L.o_restriction_3(P(ref), P(J), P(t2), C.c_int(ref.size), C.c_int(nf), C.c_int(nc))
+    du, dJ, dout = G.dev(u), G.dev(J), G.dev(np.zeros(ref.size))
+    assert G.lib.prfdd_restriction(G.p(dout), G.p(dJ), G.p(du), C.c_int(E), C.c_int(nf), C.c_int(nc), C.c_int(dim), G.stream()) == 0
+    G.sync()
+    assert np.abs(G.host(dout) - ref).max() <= 20 * TOL * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n", [1, 127, 129, 4097, 1_000_003])
+def test_vector_kernels_and_reductions(G, n):
+    rng = np.random.default_rng(n)
+    L, lib = oc.lib(), G.lib
+    a, b, c_, d = (rng.standard_normal(n) for _ in range(4))
+    m = (rng.standard_normal(n) > -0.5).astype(np.float64)
+    da, db, dc, dd, dm = (G.dev(x) for x in (a, b, c_, d, m))
+    nb = (n + 127) // 128
+    L.o_serial_sum.restype = C.c_double
+    out = G.dev(np.zeros(8))
+
+    def red_check(ref_terms, ref_val):
+        G.sync()
+        got = G.host(out)
+        tol = 4e-13 * np.abs(ref_terms).sum() + 1e-300
+        return got, tol
+
+    # residual_norm
+    blk = np.zeros(nb); L.o_residual_norm(P(blk), P(a), P(b), P(m), C.c_int(n), C.c_int(nb))
+    ref = L.o_serial_sum(P(blk), C.c_int(nb))
+    assert lib.prfdd_residual_norm(G.ws.h, G.p(out), G.p(da), G.p(db), G.p(dm), C.c_int(n), G.stream()) == 0
+    got, tol = red_check(a * b * m, ref); assert abs(got[0] - ref) <= tol
+    # projection_inner_products
+    blk = np.zeros(2 * nb); L.o_projection_inner_products(P(blk), P(a), P(b), P(c_), P(d), C.c_int(n), C.c_int(nb))
+    r0, r1 = L.o_serial_sum(P(blk), C.c_int(nb)), L.o_serial_sum(P(blk[nb:]), C.c_int(nb))
+    assert lib.prfdd_projection_inner_products(G.ws.h, G.p(out), G.p(da), G.p(db), G.p(dc), G.p(dd), C.c_int(n), G.stream()) == 0
+    got, tol = red_check(a * b, r0); assert abs(got[0] - r0) <= tol and abs(got[1] - r1) <= 4e-13 * np.abs(c_ * d).sum()
+    # inner_product_flexible
+    blk = np.zeros(nb); L.o_inner_product_flexible(P(blk), P(a), P(b), P(c_), C.c_int(n), C.c_int(nb))
+    ref = L.o_serial_sum(P(blk), C.c_int(nb))
+    assert lib.prfdd_inner_product_flexible(G.ws.h, G.p(out), G.p(da), G.p(db), G.p(dc), C.c_int(n), G.stream()) == 0
+    got, tol = red_check((b - a) * c_, ref); assert abs(got[0] - ref) <= tol
+    # inner_product with mask, weighted variants
+    blk = np.zeros(nb); L.o_inner_product_mask(P(blk), P(a), P(b), P(m), C.c_int(n), C.c_int(nb))
+    ref = L.o_serial_sum(P(blk), C.c_int(nb))
+    assert lib.prfdd_inner_product(G.ws.h, G.p(out), G.p(da), G.p(db), G.p(dm), C.c_int(n), G.stream()) == 0
+    got, tol = red_check(a * b * m, ref); assert abs(got[0] - ref) <= tol
+    assert lib.prfdd_weighted_inner_product(G.ws.h, G.p(out), G.p(da), G.p(db), G.p(dm), C.c_int(n), G.stream()) == 0
+    got, tol = red_check(a * b * m, ref); assert abs(got[0] - ref) <= tol
+    blk = np.zeros(2 * nb); L.o_sub_projection_inner_products(P(blk), P(a), P(b), P(c_), P(d), P(m), C.c_int(n), C.c_int(nb))
+    r0, r1 = L.o_serial_sum(P(blk), C.c_int(nb)), L.o_serial_sum(P(blk[nb:]), C.c_int(nb))
+    assert lib.prfdd_weighted_projection_inner_products(G.ws.h, G.p(out), G.p(da), G.p(db), G.p(dc), G.p(dd), G.p(dm), C.c_int(n), G.stream()) == 0
+    got, tol = red_check(a * b * m, r0); assert abs(got[0] - r0) <= tol and abs(got[1] - r1) <= 4e-13 * np.abs(c_ * d).sum()
+    blk = np.zeros(nb); L.o_sub_search_update_inner_product(P(blk), P(a), P(b), P(c_), P(m), C.c_int(n), C.c_int(nb))
+    ref = L.o_serial_sum(P(blk), C.c_int(nb))
+    assert lib.prfdd_search_update_inner_product(G.ws.h, G.p(out), G.p(da), G.p(db), G.p(dc), G.p(dm), C.c_int(n), G.stream()) == 0
+    got, tol = red_check((b - a) * c_ * m, ref); assert abs(got[0] - ref) <= tol
+    # multi inner product (7 vectors: exercises the 4 + 3 split) -- also checks run-to-run determinism
+    Vs = [rng.standard_normal(n) for _ in range(7)]
+    dV = [G.dev(v) for v in Vs]
+    assert lib.prfdd_multi_inner_product(G.ws.h, G.p(out), G.p(da), G.ptr_array(dV), G.p(dm), C.c_int(7), C.c_int(n), G.stream()) == 0
+    G.sync(); first = G.host(out).copy()
+    for i in range(7):
+        assert abs(first[i] - (a * Vs[i] * m).sum()) <= 4e-13 * np.abs(a * Vs[i] * m).sum() + 1e-300
+    assert lib.prfdd_multi_inner_product(G.ws.h, G.p(out), G.p(da), G.ptr_array(dV), G.p(dm), C.c_int(7), C.c_int(n), G.stream()) == 0
+    G.sync(); assert np.array_equal(first[:7], G.host(out)[:7])
+
+    # element-wise: solution_and_residual_update (value and device-scalar forms), search update, axpys
+    u_ref, r_ref = a.copy(), np.zeros(n)
+    L.o_solution_and_residual_update(P(u_ref), P(r_ref), P(b), P(c_), P(d), C.c_double(0.37), C.c_int(n))
+    du, dr = G.dev(a), G.dev(np.zeros(n))
+    assert lib.prfdd_solution_and_residual_update(G.p(du), G.p(dr), G.p(db), G.p(dc), G.p(dd), C.c_double(0.37), C.c_int(n), G.stream()) == 0
+    G.sync()
+    assert np.abs(G.host(du) - u_ref).max() <= 4e-16 * 4 and np.abs(G.host(dr) - r_ref).max() <= 1e-15 * 4
+    sc = G.dev(np.array([0.74, 2.0]))
+    du, dr = G.dev(a), G.dev(np.zeros(n))
+    assert lib.prfdd_solution_and_residual_update_dev(G.p(du), G.p(dr), G.p(db), G.p(dc), G.p(dd), C.c_void_p(sc.data_ptr()), C.c_void_p(sc.data_ptr() + 8), C.c_int(n), G.stream()) == 0
+    G.sync()
+    assert np.abs(G.host(du) - u_ref).max() <= 1e-15 * 4 and np.abs(G.host(dr) - r_ref).max() <= 1e-15 * 4
+    p_ref, r_ref = a.copy(), np.zeros(n)
+    L.o_residual_and_search_update(P(p_ref), P(r_ref), P(b), P(c_), C.c_double(-1.7), C.c_int(n))
+    dp_, dr = G.dev(a), G.dev(np.zeros(n))
+    assert lib.prfdd_residual_and_search_update(G.p(dp_), G.p(dr), G.p(db), G.p(dc), C.c_double(-1.7), C.c_int(n), G.stream()) == 0
+    G.sync()
+    assert np.abs(G.host(dp_) - p_ref).max() <= 1e-15 * 8 and np.array_equal(G.host(dr), r_ref)
+    o_ref = np.zeros(n); L.o_vector_vector_addition(P(o_ref), C.c_double(1.3), P(a), C.c_double(-0.2), P(b), C.c_int(n))
+    do = G.dev(np.zeros(n))
+    assert lib.prfdd_vector_vector_addition(G.p(do), C.c_double(1.3), G.p(da), C.c_double(-0.2), G.p(db), C.c_int(n), G.stream()) == 0
+    G.sync(); assert np.abs(G.host(do) - o_ref).max() <= 1e-15 * 8
+    assert lib.prfdd_vector_scaling(G.p(do), C.c_double(1.3), G.p(da), C.c_int(n), G.stream()) == 0
+    G.sync(); assert np.array_equal(G.host(do), 1.3 * a)
+    x = G.dev(a + 3.0)
+    assert lib.prfdd_invert_vector_elements(G.p(x), C.c_int(n), G.stream()) == 0
+    G.sync(); assert np.abs(G.host(x) - 1.0 / (a + 3.0)).max() <= 1e-15 * np.abs(1 / (a + 3)).max()
+    x = G.dev(np.zeros(n + 5))
+    assert lib.prfdd_set_to_value(G.p(x), C.c_double(2.5), C.c_int(n), C.c_int(3), G.stream()) == 0
+    G.sync(); h = G.host(x); assert np.all(h[3:3 + n] == 2.5) and np.all(h[:3] == 0) and np.all(h[3 + n:] == 0)
+    # multi axpy with device coefficients
+    coef = G.dev(np.array([0.5, -0.25, 2.0]))
+    y = G.dev(a)
+    assert lib.prfdd_multi_axpy_dev(G.p(y), G.ptr_array(dV[:3]), G.p(coef), C.c_int(1), C.c_double(-1.0), C.c_int(3), C.c_int(n), G.stream()) == 0
+    G.sync()
+    ref = ((a - 0.5 * Vs[0]) + 0.25 * Vs[1]) - 2.0 * Vs[2]
+    assert np.abs(G.host(y) - ref).max() <= 1e-15 * 16
+
+
+def test_empty_inputs(G):
+    lib = G.lib
+    z = G.dev(np.zeros(1))
+    assert lib.prfdd_set_to_value(G.p(z), C.c_double(1.0), C.c_int(0), C.c_int(0), G.stream()) == 0
+    assert lib.prfdd_stiffness_matrix(G.p(z), G.p(z), G.p(z), G.ptr_array([z] * 6), C.c_int(0), C.c_int(8), C.c_int(3), G.stream()) == 0
+    assert lib.prfdd_csr_multiply(G.p(z), G.p(z), G.p(z), G.p(z), G.p(z), C.c_int(0), C.c_int(4), G.stream()) == 0
+    out = G.dev(np.array([7.0]))
+    assert lib.prfdd_weighted_inner_product(G.ws.h, G.p(out), G.p(z), G.p(z), None, C.c_int(0), G.stream()) == 0
+    G.sync(); assert G.host(out)[0] == 0.0
+    assert lib.prfdd_stiffness_matrix(G.p(z), G.p(z), G.p(z), G.ptr_array([z] * 6), C.c_int(1), C.c_int(40), C.c_int(3), G.stream()) == -4
+
+
+@pytest.mark.parametrize("tpr", [1, 2, 4, 8, 16, 32])
+def test_csr_family(G, tpr):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(tpr)
+    lib, L = G.lib, oc.lib()
+    nr, nc = 3001, 2500
+    A = sp.random(nr, nc, density=0.004, random_state=tpr, format="csr")
+    A = (A + sp.eye(nr, nc, format="csr")).tocsr()
+    A.sort_indices()
+    ptr, col, val = A.indptr.astype(np.int32), A.indices.astype(np.int32), np.ascontiguousarray(A.data)
+    u = rng.standard_normal(nc); w = rng.standard_normal(nr); y0 = rng.standard_normal(nr)
+    dptr, dcol, dval, du, dw = (G.dev(x) for x in (ptr, col, val, u, w))
+    scale = np.abs(A) @ np.abs(u)
+    tol = 4e-15 * scale.max() + 1e-300
+    ref = np.zeros(nr); L.o_csr_multiply(P(ref), P(ptr), P(col), P(val), P(u), C.c_int(nr))
+    out = G.dev(np.zeros(nr))
+    assert lib.prfdd_csr_multiply(G.p(out), G.p(dptr), G.p(dcol), G.p(dval), G.p(du), C.c_int(nr), C.c_int(tpr), G.stream()) == 0
+    G.sync(); assert np.abs(G.host(out) - ref).max() <= tol
+    L.o_csr_multiply_weight(P(ref), P(ptr), P(col), P(val), P(u), P(w), C.c_int(nr))
+    assert lib.prfdd_csr_multiply_weight(G.p(out), G.p(dptr), G.p(dcol), G.p(dval), G.p(du), G.p(dw), C.c_int(nr), C.c_int(tpr), G.stream()) == 0
+    G.sync(); assert np.abs(G.host(out) - ref).max() <= tol * np.abs(w).max()
+    ref[:] = 0; L.o_csr_multiply_range(P(ref), P(ptr), P(col), P(val), P(u), C.c_int(100), C.c_int(2000))
+    out = G.dev(np.zeros(nr))
+    assert lib.prfdd_csr_multiply_range(G.p(out), G.p(dptr), G.p(dcol), G.p(dval), G.p(du), C.c_int(100), C.c_int(2000), C.c_int(tpr), G.stream()) == 0
+    G.sync(); assert np.abs(G.host(out) - ref).max() <= tol and G.host(out)[2001] == 0
+    assert lib.prfdd_csr_multiply_range(G.p(out), G.p(dptr), G.p(dcol), G.p(dval), G.p(du), C.c_int(5), C.c_int(4), C.c_int(tpr), G.stream()) == -7
+    ref = y0.copy(); L.o_amg_matvec(P(ref), P(ptr), P(col), P(val), P(u), C.c_double(-1.0), C.c_double(1.0), C.c_int(nr))
+    out = G.dev(y0)
+    assert lib.prfdd_csr_matvec(G.p(out), G.p(dptr), G.p(dcol), G.p(dval), G.p(du), C.c_double(-1.0), C.c_double(1.0), C.c_int(nr), C.c_int(tpr), G.stream()) == 0
+    G.sync(); assert np.abs(G.host(out) - ref).max() <= tol + 1e-15
+
+
+def test_chebyshev_smoother_matches_reference_sequence(G):
+    """One Chebyshev smoothing (order 2 and 3) through the fused kernels vs the reference's sequence
+    scaled_residual -> polynomial_evaluation -> update_field (subdomain.tpp:19-83, host branches)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(11)
+    lib, L = G.lib, oc.lib()
+    n = 4000
+    T = sp.diags([-1, 2.2, -1], [-1, 0, 1], shape=(n, n), format="csr")
+    A = (T + 0.1 * sp.random(n, n, density=0.001, random_state=1)).tocsr(); A = (A + A.T).tocsr(); A.sort_indices()
+    ptr, col, val = A.indptr.astype(np.int32), A.indices.astype(np.int32), np.ascontiguousarray(A.data)
+    ds = 1.0 / np.sqrt(A.diagonal())
+    f = rng.standard_normal(n); u0 = rng.standard_normal(n)
+    dptr, dcol, dval, dds, df = (G.dev(x) for x in (ptr, col, val, ds, f))
+    for order, coefs in ((2, [0.9, -0.35]), (3, [1.1, -0.6, 0.12])):
+        for zero_u in (True, False):
+            u = np.zeros(n) if zero_u else u0.copy()
+            r = np.zeros(n); w = np.zeros(n); v = np.zeros(n)
+            L.o_scaled_residual(P(r), P(w), P(ptr), P(col), P(val), P(u), P(f), P(ds), C.c_double(coefs[order - 1]), C.c_int(n))
+            for pidx in range(order - 2, -1, -1):
+                L.o_polynomial_evaluation(P(w), P(v), P(ptr), P(col), P(val), P(r), P(ds), C.c_double(coefs[pidx]), C.c_int(n))
+            L.o_update_field(P(u), P(w), P(ds), C.c_int(n))
+            du = G.dev(np.zeros(n) if zero_u else u0)
+            dr, dt0, dt1 = G.dev(np.zeros(n)), G.dev(np.zeros(n)), G.dev(np.zeros(n))
+            assert lib.prfdd_cheby_residual(G.p(dr), G.p(dt0), G.p(dptr), G.p(dcol), G.p(dval), None if zero_u else G.p(du), G.p(df), G.p(dds), C.c_double(coefs[order - 1]), C.c_int(n), C.c_int(4), G.stream()) == 0
+            tin, tout = dt0, dt1
+            for pidx in range(order - 2, -1, -1):
+                last = 1 if pidx == 0 else 0
+                assert lib.prfdd_cheby_step(G.p(du), G.p(tout), G.p(dptr), G.p(dcol), G.p(dval), G.p(tin), G.p(dr), G.p(dds), C.c_double(coefs[pidx]), C.c_int(last), C.c_int(1 if zero_u else 0), C.c_int(n), C.c_int(4), G.stream()) == 0
+                tin, tout = tout, tin
+            G.sync()
+            assert np.abs(G.host(du) - u).max() <= 1e-13 * np.abs(u).max()
+    # residual and dense solve
+    ref = f - A @ u0
+    dv = G.dev(np.zeros(n)); du = G.dev(u0)
+    assert lib.prfdd_csr_residual(G.p(dv), G.p(dptr), G.p(dcol), G.p(dval), G.p(du), G.p(df), C.c_int(n), C.c_int(2), G.stream()) == 0
+    G.sync(); assert np.abs(G.host(dv) - ref).max() <= 1e-13 * np.abs(ref).max()
+    M = rng.standard_normal((37, 37)); b = rng.standard_normal(37)
+    dM, db, dx = G.dev(M.ravel()), G.dev(b), G.dev(np.zeros(37))
+    assert lib.prfdd_dense_solve(G.p(dx), G.p(dM), G.p(db), C.c_int(37), G.stream()) == 0
+    G.sync(); assert np.abs(G.host(dx) - M @ b).max() <= 1e-13 * np.abs(M @ b).max()
+    # AMG/kernels.cu names
+    a, b2 = rng.standard_normal(n), rng.standard_normal(n)
+    da, db2, do1, do2 = G.dev(a), G.dev(b2), G.dev(np.zeros(n)), G.dev(np.zeros(n))
+    assert lib.prfdd_vector_multiplication(G.p(do1), G.p(da), G.p(db2), C.c_int(n), G.stream()) == 0
+    G.sync(); assert np.array_equal(G.host(do1), a * b2)
+    assert lib.prfdd_main_scaled_residual(G.p(do1), G.p(do2), G.p(da), G.p(db2), C.c_double(0.3), C.c_int(n), G.stream()) == 0
+    G.sync(); assert np.array_equal(G.host(do1), b2 * a) and np.allclose(G.host(do2), 0.3 * (b2 * a), rtol=1e-15)
+    dvv = G.dev(a.copy())
+    assert lib.prfdd_main_polynomial_evaluation(G.p(do1), G.p(dvv), G.p(db2), G.p(dds), C.c_double(0.7), C.c_int(n), G.stream()) == 0
+    G.sync(); assert np.allclose(G.host(do1), 0.7 * b2 + a * ds, rtol=1e-14, atol=1e-15)
+    duu = G.dev(a.copy())
+    assert lib.prfdd_main_update_field(G.p(duu), G.p(db2), G.p(dds), C.c_int(n), G.stream()) == 0
+    G.sync(); assert np.allclose(G.host(duu), a + ds * b2, rtol=1e-14, atol=1e-15)
+    assert lib.prfdd_vector_set_to_value(G.p(duu), C.c_double(4.0), C.c_int(n), G.stream()) == 0
+    G.sync(); assert np.all(G.host(duu) == 4.0)
+
+
+def test_gather_scatter_and_halo(G):
+    rng = np.random.default_rng(2)
+    lib = G.lib
+    npts, nn = 50000, 17000
+    node_of_point = rng.integers(0, nn, npts).astype(np.int32)
+    node_of_point[:nn] = np.arange(nn)             # every node touched
+    order = np.argsort(node_of_point, kind="stable")
+    ptr = np.zeros(nn + 1, np.int32); np.add.at(ptr, node_of_point + 1, 1); ptr = np.cumsum(ptr).astype(np.int32)
+    col = order.astype(np.int32)
+    u = rng.standard_normal(npts); w = rng.standard_normal(nn); m = (rng.standard_normal(npts) > 0).astype(np.float64)
+    L = oc.lib()
+    ref_nodes = np.zeros(nn)
+    L.o_csr_multiply_weight(P(ref_nodes), P(ptr), P(col), P(np.ones(npts)), P(u), P(w), C.c_int(nn))
+    dn = G.dev(np.zeros(nn))
+    assert lib.prfdd_gather(G.p(dn), G.p(G.dev(ptr)), G.p(G.dev(col)), G.p(G.dev(u)), G.p(G.dev(w)), C.c_int(nn), G.stream()) == 0
+    G.sync(); assert np.abs(G.host(dn) - ref_nodes).max() <= 1e-14 * np.abs(ref_nodes).max()
+    dout = G.dev(np.zeros(npts))
+    assert lib.prfdd_scatter(G.p(dout), G.p(G.dev(node_of_point)), G.p(dn), G.p(G.dev(m)), C.c_int(npts), G.stream()) == 0
+    G.sync(); assert np.array_equal(G.host(dout), G.host(dn)[node_of_point] * m)
+    idx = np.sort(rng.choice(nn, 999, replace=False)).astype(np.int32)
+    buf = G.dev(np.zeros(999))
+    assert lib.prfdd_halo_pack(G.p(buf), G.p(dn), G.p(G.dev(idx)), C.c_int(999), G.stream()) == 0
+    G.sync(); assert np.array_equal(G.host(buf), G.host(dn)[idx])
+    before = G.host(dn).copy()
+    assert lib.prfdd_halo_unpack_add(G.p(dn), G.p(buf), G.p(G.dev(idx)), C.c_int(999), G.stream()) == 0
+    G.sync(); after = before.copy(); after[idx] += before[idx]
+    assert np.array_equal(G.host(dn), after)
