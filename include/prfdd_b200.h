@@ -48,6 +48,8 @@ int prfdd_set_device(int device);
 /* number of kernel launches issued by this library since the last reset (bench.py "gpu_launches") */
 long long prfdd_launch_count(void);
 void prfdd_launch_count_reset(void);
+/* kernels replayed from a captured CUDA graph are counted through this */
+void prfdd_launch_count_add(long long n);
 
 /* replaces occa::memory malloc / free / copyFrom / copyTo / device.finish */
 int prfdd_malloc(void **dptr, size_t bytes);
@@ -219,6 +221,58 @@ int prfdd_search_update_inner_product(prfdd_reduce_ws *ws, double *out, const do
                                       const double *z_k, const double *weight, int n, prfdd_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * device-resident Krylov bookkeeping: the Hessenberg / Givens / back-substitution scalars of the
+ * inner flexible GMRES (subdomain.tpp:4404-4470) and the alpha/beta of the inner flexible CG
+ * (subdomain.tpp:4215, 4256) live in this struct IN DEVICE MEMORY and are updated by one-thread
+ * kernels, so an entire preconditioner application runs without a host synchronisation and can be
+ * captured in a CUDA graph.  Vector kernels read their coefficients through pointers into it.
+ * ------------------------------------------------------------------------------------------- */
+#define PRFDD_KRYLOV_MAXV 32
+typedef struct prfdd_krylov_state
+{
+    double H[(PRFDD_KRYLOV_MAXV + 1) * PRFDD_KRYLOV_MAXV]; /* H[i*MAXV + j] */
+    double c[PRFDD_KRYLOV_MAXV];
+    double s[PRFDD_KRYLOV_MAXV];
+    double gamma[PRFDD_KRYLOV_MAXV + 1];
+    double hcol[PRFDD_KRYLOV_MAXV + 1]; /* raw Gram-Schmidt dots of the current column */
+    double y[PRFDD_KRYLOV_MAXV];        /* back-substituted coefficients (0 beyond the last column used) */
+    double red[8];                      /* scratch for reductions: red[0] norm^2, red[0..1] gamma/theta ... */
+    double r0_norm;
+    double inv_gamma0;                  /* 1 / gamma[0] */
+    double inv_alpha;                   /* 1 / alpha_j */
+    double alpha_cg;                    /* inner FCG: alpha_k (0 once stopped) */
+    double beta_cg;
+    double gamma_cg;
+    double r_norm;
+    double one;                         /* constant 1.0 (denominator for *_dev kernels) */
+    int stopped;                        /* set when a break condition of the reference fired */
+    int cycle_active;
+    int j_last;                         /* last Arnoldi column whose Z is used */
+    int iterations;                     /* accumulated like Subdomain::num_iterations */
+} prfdd_krylov_state;
+
+int prfdd_krylov_reset(prfdd_krylov_state *st, prfdd_stream_t stream);           /* new solve: stopped = 0 */
+/* gamma[0] = sqrt(red[0]); first cycle: r0_norm = gamma[0]; inv_gamma0 = 1/gamma[0]  (tpp:4343-4365) */
+int prfdd_gmres_begin_cycle(prfdd_krylov_state *st, int first_cycle, prfdd_stream_t stream);
+/* column j: H[0..j][j] = hcol, Givens, alpha = sqrt(red[0]), stop tests of tpp:4415-4453 */
+int prfdd_gmres_column(prfdd_krylov_state *st, int j, int iter, int max_iterations, double tolerance,
+                       int use_relative, prfdd_stream_t stream);
+/* back-substitution (tpp:4460-4470) into y[]; y = 0 for a cycle that started after convergence */
+int prfdd_gmres_end_cycle(prfdd_krylov_state *st, int num_vectors, prfdd_stream_t stream);
+/* inner FCG scalars: alpha = red[0]/red[1] (gamma/theta) unless stopped                 (tpp:4215) */
+int prfdd_fcg_alpha(prfdd_krylov_state *st, prfdd_stream_t stream);
+/* r_norm = sqrt(red[2]); stop tests of tpp:4231-4240; iterations++ */
+int prfdd_fcg_check(prfdd_krylov_state *st, int iter, int max_iterations, double tolerance, int use_relative,
+                    prfdd_stream_t stream);
+/* beta = red[3]/gamma (tpp:4256) unless stopped (then beta = 0 and p, r are left untouched by callers) */
+int prfdd_fcg_beta(prfdd_krylov_state *st, prfdd_stream_t stream);
+/* y += a*x with a read from device memory; nothing happens when *a == 0 exactly */
+int prfdd_axpy_dev(double *y, const double *a, double sign, const double *x, int n, prfdd_stream_t stream);
+/* p = z + beta p ; r = r1, skipped entirely when *skip_flag != 0                       subdomain.okl:259-266 */
+int prfdd_residual_and_search_update_gated(double *p_k, double *r_k, const double *z_k, const double *r_kp1,
+                                           const double *beta, const int *skip_flag, int n, prfdd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * special functions (special_functions.hpp:10-12; host, C++ restatement of Nek5000 speclib)
  * ------------------------------------------------------------------------------------------- */
 void prfdd_zwgll(double *z, double *w, int np);
@@ -237,6 +291,26 @@ void prfdd_glibc_rand_fill(double *out, long long n, unsigned int seed);
  * block-partitioned over num_procs ranks (power of two); eps = smooth deformation amplitude */
 int prfdd_mesh_generate_box(const char *directory, int dim, const int nel[3], int poly_degree, int num_procs,
                             double eps);
+
+/* ---------------------------------------------------------------------------------------------
+ * AMG setup on the HOST (no device needed): the library's deterministic stand-in for the two
+ * HYPRE_BoomerAMGSetup calls of the reference (subdomain.tpp:1851-1858, 3480-3489).  Exposed so the
+ * hierarchy (C/F splittings, interpolation, Galerkin operators, Chebyshev data) can be inspected and
+ * compared with the oracle without a GPU.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct prfdd_amg_host prfdd_amg_host;
+int prfdd_amg_host_setup(prfdd_amg_host **h, int n, const int *ptr, const int *col, const double *val, int cheby_order,
+                         int max_coarse_size);
+int prfdd_amg_host_destroy(prfdd_amg_host *h);
+int prfdd_amg_host_num_levels(const prfdd_amg_host *h);
+/* sizes[0..3] = rows of A_l, nnz of A_l, columns of P_l (0 on the last level), nnz of P_l */
+int prfdd_amg_host_level_sizes(const prfdd_amg_host *h, int level, int sizes[4]);
+/* which: 0 = A_l, 1 = P_l.  Copies ptr (rows+1), col, val */
+int prfdd_amg_host_get_matrix(const prfdd_amg_host *h, int level, int which, int *ptr, int *col, double *val);
+/* cf (rows, +1 C / -1 F; empty on the last level), ds (rows), coefs (cheby_order), eigs (max, min) */
+int prfdd_amg_host_get_vectors(const prfdd_amg_host *h, int level, signed char *cf, double *ds, double *coefs, double eigs[2]);
+/* dense inverse of the coarsest operator, row-major rows x rows */
+int prfdd_amg_host_get_coarse_inverse(const prfdd_amg_host *h, double *Ainv);
 
 /* ---------------------------------------------------------------------------------------------
  * solver objects: the reference's run_simulation() sequence (poisson.cpp:150-251) behind handles

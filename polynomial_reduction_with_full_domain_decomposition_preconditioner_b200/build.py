@@ -19,7 +19,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--extended-lambda", "-I/usr/include"]
 
-CU_SOURCES = ["k_vector.cu", "k_sem.cu", "k_sparse.cu"]
+CU_SOURCES = ["k_vector.cu", "k_sem.cu", "k_sparse.cu", "k_krylov.cu"]
 CPP_SOURCES = ["host/special_functions.cpp", "host/globals.cpp", "host/comm.cpp", "host/mesh.cpp", "host/capi.cpp"]
 
 

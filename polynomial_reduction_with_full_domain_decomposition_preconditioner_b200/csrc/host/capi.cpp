@@ -302,6 +302,70 @@ int prfdd_solver_apply(prfdd_solver *s, int what, const double *in_host, double 
     });
 }
 
+// ---- host-only AMG setup handle ------------------------------------------------------------
+struct prfdd_amg_host
+{
+    amg::Hierarchy H;
+};
+
+int prfdd_amg_host_setup(prfdd_amg_host **h, int n, const int *ptr, const int *col, const double *val, int cheby_order, int max_coarse_size)
+{
+    try
+    {
+        amg::HostCSR A;
+        A.num_rows = A.num_cols = n;
+        A.ptr.assign(ptr, ptr + n + 1);
+        A.col.assign(col, col + ptr[n]);
+        A.val.assign(val, val + ptr[n]);
+        prfdd_amg_host *o = new prfdd_amg_host();
+        o->H.setup(std::move(A), cheby_order, max_coarse_size, 0.25, 4, 25, /*on_device=*/false);
+        *h = o;
+        return 0;
+    }
+    catch (const std::exception &ex)
+    {
+        fprintf(stderr, "prfdd_amg_host_setup: %s\n", ex.what());
+        return -1;
+    }
+}
+
+int prfdd_amg_host_destroy(prfdd_amg_host *h) { delete h; return 0; }
+int prfdd_amg_host_num_levels(const prfdd_amg_host *h) { return h->H.num_levels(); }
+
+int prfdd_amg_host_level_sizes(const prfdd_amg_host *h, int level, int sizes[4])
+{
+    const amg::Level &L = h->H.levels[level];
+    sizes[0] = L.n; sizes[1] = L.A.nnz(); sizes[2] = L.P.num_cols; sizes[3] = L.P.nnz();
+    return 0;
+}
+
+int prfdd_amg_host_get_matrix(const prfdd_amg_host *h, int level, int which, int *ptr, int *col, double *val)
+{
+    const amg::Level &L = h->H.levels[level];
+    const amg::HostCSR &M = which == 0 ? L.A : L.P;
+    if (M.ptr.empty()) return -1;
+    std::copy(M.ptr.begin(), M.ptr.end(), ptr);
+    std::copy(M.col.begin(), M.col.end(), col);
+    std::copy(M.val.begin(), M.val.end(), val);
+    return 0;
+}
+
+int prfdd_amg_host_get_vectors(const prfdd_amg_host *h, int level, signed char *cf, double *ds, double *coefs, double eigs[2])
+{
+    const amg::Level &L = h->H.levels[level];
+    if (cf) std::copy(L.cf.begin(), L.cf.end(), cf);
+    if (ds) std::copy(L.ds_hst.begin(), L.ds_hst.end(), ds);
+    if (coefs) std::copy(L.coefs.begin(), L.coefs.end(), coefs);
+    if (eigs) { eigs[0] = L.max_eig; eigs[1] = L.min_eig; }
+    return 0;
+}
+
+int prfdd_amg_host_get_coarse_inverse(const prfdd_amg_host *h, double *Ainv)
+{
+    std::copy(h->H.Ainv_hst.begin(), h->H.Ainv_hst.end(), Ainv);
+    return 0;
+}
+
 double prfdd_solver_timer_total(prfdd_solver *s, const char *key)
 {
     if (!strcmp(key, "__enable__")) { s->tmr.enabled = true; return 0.0; }

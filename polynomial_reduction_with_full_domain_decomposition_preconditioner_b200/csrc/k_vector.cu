@@ -149,6 +149,7 @@ int prfdd_reduce_ws_destroy(prfdd_reduce_ws *ws)
 
 long long prfdd_launch_count(void) { return g_launch_count; }
 void prfdd_launch_count_reset(void) { g_launch_count = 0; }
+void prfdd_launch_count_add(long long n) { g_launch_count += n; }
 
 // ------------------------------------------------------------------------------ math.okl
 int prfdd_set_to_value(double *u, double alpha, int n, int offset, prfdd_stream_t stream)
@@ -198,7 +199,11 @@ int prfdd_multi_axpy_dev(double *y, const double *const *X, const double *coef, 
     // vector_vector_addition calls (domain.tpp:817-822, 902-907; subdomain.tpp:4396-4401, 4473-4478)
     return map(n, S(stream), [=] __device__(long long i) {
         double acc = y[i];
-        for (int k = 0; k < count; k++) acc = acc + (sign * coef[k * coef_stride]) * pk.p[k][i];
+        for (int k = 0; k < count; k++)
+        {
+            const double c = sign * coef[k * coef_stride];
+            if (c != 0.0) acc = acc + c * pk.p[k][i]; // columns beyond the last one used carry c == 0 exactly
+        }
         y[i] = acc;
     });
 }

@@ -1,0 +1,94 @@
+"""-m gpu: the PR-FDD preconditioned solve on the GPU (one rank) against the oracle on the same mesh files.
+Bit-exact integer maps (region dof numbering, Q structure, AMG level sizes), low-order FEM matrix to 1e-12,
+every building block (composite operator, V-cycle, low-order preconditioner, one inner Krylov solve) to 1e-10,
+and the headline: same outer PCG iteration count, same residual history, solution within 1e-10 relative L2
+(the north-star tolerance), for both inner solvers and both outer drivers."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+from oracle import domain as odomain, subdomain as osub  # noqa: E402
+
+CASES = [(2, 4, 4, 3, 0.0), (2, 8, 7, 3, 0.05), (2, 16, 7, 3, 0.0), (3, 3, 4, 3, 0.05), (3, 2, 7, 6, 0.03), (3, 4, 7, 3, 0.0), (3, 3, 2, 1, 0.04), (2, 5, 1, 1, 0.1)]
+
+
+def _need_gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+@pytest.mark.parametrize("dim,nel,N,r,eps", CASES)
+def test_preconditioned_parity(prfdd, tmp_path, dim, nel, N, r, eps):
+    _need_gpu()
+    d = str(tmp_path)
+    prfdd.mesh_generate_box(d, dim, nel, N, 1, eps, reduction=r)
+    W = odomain.DomainWorld(d, N, 1)
+    Sd = osub.SubdomainWorld(W, d, N, r)
+    So = Sd.ranks[0]
+    S = prfdd.Solver(d, poly_degree=N, poly_reduction=r)
+    # integer maps: bit exact
+    assert S.query("SUB_NUM_POINTS") == So.num_points and S.query("SUB_NUM_DOFS") == So.sub_num_dofs
+    assert S.query("SUB_NUM_EXTENDED_DOFS") == So.sub_num_extended_dofs and S.query("NUM_DOFS") == So.num_dofs
+    assert S.query("NUM_VALUES") == So.num_values and S.query("SUP_NUM_EXTENDED_DOFS") == 0
+    assert np.array_equal(S.get_array("SUB_DOF_NUM"), So.dof_num)
+    assert np.array_equal(S.get_array("SUB_ELEMENT_IDS"), So.elem_id) and np.array_equal(S.get_array("SUB_ELEMENT_DEGREE"), So.elem_degree)
+    assert np.array_equal(S.get_array("SUB_Q_PTR"), So.Q.ptr) and np.array_equal(S.get_array("SUB_Q_COL"), So.Q.col)
+    assert np.array_equal(S.get_array("SUB_Q_VAL"), So.Q.val)
+    assert np.array_equal(S.get_array("NORM_WEIGHT"), So.norm_weight) and np.array_equal(S.get_array("INNER_WEIGHT"), So.inner_weight)
+    # low-order FEM matrix and AMG hierarchy
+    A = sp.csr_matrix((S.get_array("A_FEM_VAL"), S.get_array("A_FEM_COL"), S.get_array("A_FEM_PTR")), shape=(So.num_dofs, So.num_dofs))
+    assert (A != 0).nnz == (So.A_fem != 0).nnz
+    assert abs(A - So.A_fem).max() <= 1e-12 * abs(So.A_fem).max()
+    assert np.array_equal(S.get_array("AMG_LEVEL_ROWS"), [L.n for L in So.amg.levels])
+    assert np.array_equal(S.get_array("AMG_LEVEL_NNZ"), [L.A.nnz for L in So.amg.levels])
+    assert np.allclose(S.get_array("AMG_CHEBY_COEFS"), np.concatenate([L.coefs for L in So.amg.levels]), rtol=1e-8)
+    # building blocks
+    rng = np.random.default_rng(3)
+    nvl = So.num_values
+    x = rng.standard_normal(nvl)
+    ref = np.zeros(nvl); Sd.stiffness_matrix(So, ref, x)
+    assert np.abs(S.apply("SUB_STIFFNESS", x) - ref).max() <= 1e-12 * np.abs(ref).max()
+    b = rng.standard_normal(So.num_dofs)
+    ref = So.amg.vcycle(b, 1)
+    got = S.apply("VCYCLE", b)
+    assert np.abs(got - ref).max() <= 1e-10 * np.abs(ref).max()
+    ref = np.zeros(nvl); Sd.low_order_preconditioner(So, ref, x)
+    got = S.apply("LOW_ORDER", x)
+    assert np.abs(got - ref).max() <= 1e-10 * np.abs(ref).max()
+    P_ = W.ranks[0].num_local_points
+    rr = rng.standard_normal(P_)
+    for ptype, fn in ((1, Sd.generalized_minimum_residual), (0, Sd.flexible_conjugate_gradient)):
+        zo = [np.zeros(P_)]; fn(zo, [rr])
+        Sx = prfdd.Solver(d, poly_degree=N, poly_reduction=r, preconditioner_type=ptype)
+        for _ in range(2):   # second call replays the captured CUDA graph
+            zg = Sx.apply("PRECONDITIONER", rr)
+            assert np.linalg.norm(zg - zo[0]) <= 1e-9 * np.linalg.norm(zo[0])
+        Sx.close()
+    # the solve
+    S.setup_problem(4)
+    us = W.initial_function(4)
+    f = W.new_vector(); W.stiffness_matrix(f, us)
+    for ptype in (1, 0):
+        W.preconditioner_type = ptype
+        Sx = prfdd.Solver(d, poly_degree=N, poly_reduction=r, preconditioner_type=ptype)
+        Sx.setup_problem(4)
+        for solver_id, drv in ((0, W.flexible_conjugate_gradient), (1, W.generalized_minimum_residual)):
+            u = W.new_vector(); drv(u, f, Sd)
+            nit, hist = Sx.solve(solver_id)
+            assert nit == W.num_iterations, (nit, W.num_iterations)
+            assert np.abs(hist - np.array(W.history)).max() <= 1e-9 * W.history[0]
+            ug = Sx.get_array("U")
+            assert np.linalg.norm(ug - u[0]) <= 1e-10 * np.linalg.norm(u[0])
+            assert np.linalg.norm(ug - us[0]) <= 1e-5 * np.linalg.norm(us[0])
+            assert hist[-1] / hist[0] < 1e-7
+        Sx.close()
+    # graph and no-graph paths agree bit for bit
+    S1 = prfdd.Solver(d, poly_degree=N, poly_reduction=r, use_cuda_graph=0); S1.setup_problem(4)
+    S2 = prfdd.Solver(d, poly_degree=N, poly_reduction=r, use_cuda_graph=1); S2.setup_problem(4)
+    n1, h1 = S1.solve(0); n2, h2 = S2.solve(0)
+    assert n1 == n2 and np.array_equal(h1, h2) and np.array_equal(S1.get_array("U"), S2.get_array("U"))
+    assert S2.query("GPU_LAUNCHES_PER_PRECOND") > 0
+    S1.close(); S2.close(); S.close()
