@@ -16,6 +16,7 @@ struct prfdd_solver
     prfdd_options opt;
     std::string directory;
     cudaStream_t stream = nullptr;
+    bool own_stream = false;
     int device_id = 0;
     int dim_ = 0;
     std::map<int, std::unique_ptr<Domain<STYPE>>> domains; // ladder of Domain objects (poisson.cpp:172-199)
@@ -99,6 +100,12 @@ int prfdd_solver_create(prfdd_solver **out, const char *directory, const prfdd_o
     s->directory = directory;
     s->stream = (cudaStream_t)stream;
     cudaGetDevice(&s->device_id);
+    if (s->stream == nullptr)
+    {
+        // the legacy default stream cannot be captured into a CUDA graph: run on an own stream instead
+        if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return -1; }
+        s->own_stream = true;
+    }
     int rc = guarded(nullptr, [&]() {
         s->comm.init(opt->proc_id, opt->num_procs, opt->nccl_unique_id, s->stream);
         s->tmr.stream = s->stream;
@@ -172,6 +179,7 @@ int prfdd_solver_destroy(prfdd_solver *s)
         s->comm.finalize();
         return 0;
     });
+    if (s->own_stream) cudaStreamDestroy(s->stream);
     delete s;
     return 0;
 }
