@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the PR-FDD preconditioned CG hot path (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+    python bench.py --impl reference --gpus N ...            # the reference algorithm on the host CPU (oracle port)
+
+metric   FP64 PCG GDOF*iter/s  = (global unique GLL nodes x outer PCG iterations) / solve time / 1e9
+step     one complete preconditioned CG solve (flexible CG, relative residual 1e-8) of the synthetic problem
+         f = A u*, u* = glibc rand() stream (the reference's function_id 4), through the C ABI
+workload N = 1: BASELINE configs[1] -- 3D SEM Poisson, 16^3 hex box mesh, polynomial degree 7, FP64
+         N > 1: weak scaling, 16^3 elements per GPU, block partition (N = 8 is configs[2]: 32^3 on 2x2x2)
+value    device-resident f (only the residual norm is read by the host each iteration)
+e2e      the same solve through prfdd_solver_solve_host: f copied host->device and u device->host inside
+         the timed region, every step
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "fp64_pcg_gdof_iter_per_s"
+UNIT = "GDOF*iter/s"
+TOL = 1.0e-8            # BASELINE.json: "iters to 1e-8" (the reference's own default is 1e-7, domain.hpp:118)
+N_DEG, REDUCTION = 7, 3  # degree ladder 7, 4, 1 (profile.sh:5-11)
+NEL_PER_GPU = 16
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def layout(nranks):
+    p = [1, 1, 1]
+    d, r = 0, nranks
+    while r > 1:
+        p[d % 3] *= 2
+        r //= 2
+        d += 1
+    return p
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host CPU.  The reference itself cannot be built here
+    (OCCA / HYPRE / GSLib / MPI / gfortran absent), so this is the oracle port -- plain C kernels (the loops
+    OCCA Serial runs) driven by the restated Domain / Subdomain control flow -- on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import meshgen, domain as od, subdomain as osub
+    nel = args.cpu_nel
+    d = tempfile.mkdtemp(prefix="prfdd_ref_")
+    for n in osub.ladder(N_DEG, REDUCTION):
+        meshgen.generate(d, 3, nel, n, nranks=1, eps=0.0)
+    W = od.DomainWorld(d, N_DEG, 1)
+    W.tolerance = TOL
+    Sd = osub.SubdomainWorld(W, d, N_DEG, REDUCTION)
+    us = W.initial_function(4)
+    f = W.new_vector(); W.stiffness_matrix(f, us)
+    nodes = (nel * N_DEG + 1) ** 3
+    for _ in range(args.warmup):
+        u = W.new_vector(); W.flexible_conjugate_gradient(u, f, Sd)
+    t0 = time.perf_counter()
+    iters = 0
+    for _ in range(args.steps):
+        u = W.new_vector(); W.flexible_conjugate_gradient(u, f, Sd)
+        iters += len(W.history) - 1
+    dt = time.perf_counter() - t0
+    value = nodes * iters / dt / 1e9
+    sample = "3D %d^3 hex box, N=7 (%d nodes), full PR-FDD PCG solve to 1e-8, %d solve(s); setup excluded" % (nel, nodes, args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D SEM Poisson PR-FDD PCG, N=7, ladder 7/4/1 (CPU sample: %d^3 elements)" % nel, "tolerance": TOL},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "iterations": iters // max(args.steps, 1)}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(nel):
+    from oracle import meshgen, domain as od, subdomain as osub
+    d = tempfile.mkdtemp(prefix="prfdd_cpu_")
+    for n in osub.ladder(N_DEG, REDUCTION):
+        meshgen.generate(d, 3, nel, n, nranks=1, eps=0.0)
+    W = od.DomainWorld(d, N_DEG, 1)
+    W.tolerance = TOL
+    Sd = osub.SubdomainWorld(W, d, N_DEG, REDUCTION)
+    us = W.initial_function(4)
+    f = W.new_vector(); W.stiffness_matrix(f, us)
+    nodes = (nel * N_DEG + 1) ** 3
+    u = W.new_vector(); W.flexible_conjugate_gradient(u, f, Sd)     # warm
+    t0 = time.perf_counter(); iters = 0; reps = 0
+    while time.perf_counter() - t0 < 10.0 and reps < 5:
+        u = W.new_vector(); W.flexible_conjugate_gradient(u, f, Sd)
+        iters += len(W.history) - 1; reps += 1
+    dt = time.perf_counter() - t0
+    return {"value": nodes * iters / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle port (C kernels = OCCA-Serial loops) on the box's host CPU: 3D %d^3 hex box, N=7 (%d nodes), %d full PR-FDD PCG solves to 1e-8, setup excluded" % (nel, nodes, reps)}
+
+
+def kernel_roofline(pr, torch, stream, peaks, peaks_kind):
+    """average launch duration of the dominant kernel, measured with CUDA events on the launching stream,
+    on device data of the workload's size: the fused Chebyshev SpMV step on the level-0 low-order FEM matrix
+    is not reachable from outside the solver, so the SEM operator (the dominant single kernel of the outer
+    iteration and of every Arnoldi step) is timed here; profiles/ holds the per-kernel shares."""
+    L = pr.lib()
+    E, n = NEL_PER_GPU ** 3, N_DEG + 1
+    P = E * n ** 3
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    u = torch.rand(P, dtype=torch.float64, device="cuda", generator=g)
+    G = [torch.rand(P, dtype=torch.float64, device="cuda", generator=g) for _ in range(6)]
+    Au = torch.empty(P, dtype=torch.float64, device="cuda")
+    z = np.zeros(n); w = np.zeros(n); D = np.zeros(n * n)
+    L.prfdd_zwgll(z.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), C.c_int(n))
+    L.prfdd_dgll(D.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), C.c_int(n))
+    Dd = torch.from_numpy(D).cuda()
+    gp = (C.c_void_p * 6)(*[t.data_ptr() for t in G])
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+    sh = C.c_void_p(stream.cuda_stream)
+    times = []
+    with torch.cuda.stream(stream):
+        for it in range(13):
+            flush.fill_(float(it))                      # evict the 126 MB L2 between timed launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rc = L.prfdd_stiffness_matrix(C.c_void_p(Au.data_ptr()), C.c_void_p(u.data_ptr()), C.c_void_p(Dd.data_ptr()), gp, C.c_int(E), C.c_int(n), C.c_int(3), sh)
+            e1.record(stream)
+            assert rc == 0
+            stream.synchronize()
+            if it >= 3:
+                times.append(e0.elapsed_time(e1))
+    t_ms = float(np.mean(times))
+    bytes_alg = 64.0 * P                                  # u 8 + six G 48 + Au 8 per point
+    achieved = bytes_alg / (t_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "k_ax3d<8,2> (prfdd_stiffness_matrix, 4096 elements, n=8)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peaks_kind == "measured" else "fallback 6.65 TB/s",
+            "avg_launch_ms": t_ms, "algorithmic_bytes_per_launch": bytes_alg}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-nel", type=int, default=6, help="elements per side of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eps", type=float, default=0.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    import polynomial_reduction_with_full_domain_decomposition_preconditioner_b200 as pr
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    L = pr.lib()
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # one ncclUniqueId for the library's own communicator, broadcast with the torch process group
+        holder = [None]
+        if rank == 0:
+            import ctypes.util
+            nccl = C.CDLL("libnccl.so.2")
+            buf = C.create_string_buffer(128)
+            assert nccl.ncclGetUniqueId(buf) == 0
+            holder[0] = bytes(buf.raw)
+        dist.broadcast_object_list(holder, src=0)
+        uid = holder[0]
+
+    # synthetic mesh in the reference's on-disk format: every rank's files, written once by rank 0
+    P3 = layout(world)
+    nel = [NEL_PER_GPU * P3[0], NEL_PER_GPU * P3[1], NEL_PER_GPU * P3[2]]
+    if world > 1:
+        holder = [tempfile.mkdtemp(prefix="prfdd_bench_") if rank == 0 else None]
+        dist.broadcast_object_list(holder, src=0)
+        mesh_dir = holder[0]
+    else:
+        mesh_dir = tempfile.mkdtemp(prefix="prfdd_bench_")
+    use_pc = 1 if world == 1 else 0      # multi-rank PR-FDD setup: not built yet, N > 1 runs unpreconditioned
+    t_setup0 = time.perf_counter()
+    if rank == 0:
+        pr.mesh_generate_box(mesh_dir, 3, tuple(nel), N_DEG, world, args.eps, reduction=REDUCTION if use_pc else None)
+    if world > 1:
+        dist.barrier()
+
+    stream = torch.cuda.Stream()
+    S = pr.Solver(mesh_dir, stream=stream.cuda_stream, poly_degree=N_DEG, poly_reduction=REDUCTION, use_preconditioner=use_pc,
+                  outer_tolerance=TOL, proc_id=rank, num_procs=world, nccl_unique_id=uid)
+    S.setup_problem(4)
+    stream.synchronize()
+    setup_s = time.perf_counter() - t_setup0
+    nodes = S.query("NUM_GLOBAL_NODES")
+    P = S.query("NUM_LOCAL_POINTS")
+    f_host = torch.from_numpy(S.get_array("F")).pin_memory()
+    u_host = torch.empty(P, dtype=torch.float64).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        L.prfdd_launch_count_reset()
+        e0.record(stream)
+        iters = 0
+        for _ in range(steps):
+            iters += fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = int(L.prfdd_launch_count())
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, iters, launches
+
+    def step_dev():
+        nit, hist = S.solve(0)
+        return len(hist) - 1
+
+    def step_host():
+        nit, hist = S.solve_host(f_host.numpy(), u_host.numpy(), 0)
+        return len(hist) - 1
+
+    for _ in range(args.warmup):
+        step_dev()
+    for _ in range(2):
+        step_host()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, iters, launches = timed(step_dev, args.steps)
+    ms_e2e, iters_e2e, _ = timed(step_host, args.steps)
+    clocks = sampler.stop()
+    value = nodes * iters / (ms * 1e-3) / 1e9
+    e2e = nodes * iters_e2e / (ms_e2e * 1e-3) / 1e9
+    nit, hist = S.solve(0)
+    err = None
+    if rank == 0:
+        us, ug = S.get_array("U_STAR"), S.get_array("U")
+        err = float(np.linalg.norm(ug - us) / np.linalg.norm(us))
+
+    if rank == 0:
+        peaks, kind = measured_peaks()
+        roof = kernel_roofline(pr, torch, stream, peaks, kind)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(args.cpu_nel)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "3D SEM Poisson, %dx%dx%d hex box mesh, N=7, FP64, PR-FDD preconditioned flexible CG (ladder 7/4/1, overlaps 1/1, inner GMRES(4), 1 V-cycle, Chebyshev order 2)" % tuple(nel)
+                           if use_pc else "3D SEM Poisson, %dx%dx%d hex box mesh, N=7, FP64, flexible CG WITHOUT the PR-FDD preconditioner (multi-rank preconditioner setup not built yet)" % tuple(nel),
+                           "tolerance": TOL, "global_nodes": nodes, "iterations_per_solve": iters // args.steps, "l2": "working set (geometry 96 MiB + vectors + AMG hierarchy) exceeds the 126 MB L2",
+                           "partition": "%dx%dx%d blocks of 16^3 elements" % tuple(P3), "time_to_solution_ms": ms / args.steps, "setup_s": setup_s, "rel_error_vs_exact": err},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * P * world, "d2h_bytes_per_step": 8 * P * world, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    S.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,75 @@
+// poisson.cpp -- the driver with the reference's command line and log lines
+//   poisson <directory> <polynomial degree> <polynomial reduction> <subdomain overlap> <superdomain overlap> [solver_id]
+// (/root/reference/poisson.cpp:40-81, 150-251).  Single process = single GPU; multi-GPU runs are launched one process
+// per GPU with PRFDD_RANK / PRFDD_NRANKS / PRFDD_NCCL_ID_FILE in the environment (rank 0 writes the ncclUniqueId file).
+#include "../../../include/prfdd_b200.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+int main(int argc, char *argv[])
+{
+    if (argc < 6)
+    {
+        printf("ERROR: Use as 'poisson <directory> <polynomial degree> <polynomial reduction> <subdomain overlap> <superdomain overlap>'\n");
+        return EXIT_SUCCESS; // the reference's quit() exits with EXIT_SUCCESS (config.hpp:57-62)
+    }
+    printf("----------------------------------------------------------------------------------\n");
+    printf("|  Full domain decomposition with polynomial reduction -- B200-native build      |\n");
+    printf("----------------------------------------------------------------------------------\n\n");
+    prfdd_options opt;
+    prfdd_options_default(&opt);
+    opt.poly_degree = atoi(argv[2]);
+    opt.poly_reduction = atoi(argv[3]);
+    opt.subdomain_overlap = atoi(argv[4]);
+    opt.superdomain_overlap = atoi(argv[5]);
+    opt.verbose = 1;
+    const int solver_id = argc > 6 ? atoi(argv[6]) : 1; // poisson.cpp:224 ships solver_id = 1 (GMRES); 0 = FCG
+    if (getenv("PRFDD_TOLERANCE")) opt.outer_tolerance = atof(getenv("PRFDD_TOLERANCE"));
+    if (getenv("PRFDD_NO_PRECONDITIONER")) opt.use_preconditioner = 0;
+    if (getenv("PRFDD_INNER_FCG")) opt.preconditioner_type = 0;
+    unsigned char id[128];
+    if (getenv("PRFDD_NRANKS") && atoi(getenv("PRFDD_NRANKS")) > 1)
+    {
+        opt.num_procs = atoi(getenv("PRFDD_NRANKS"));
+        opt.proc_id = atoi(getenv("PRFDD_RANK"));
+        FILE *f = fopen(getenv("PRFDD_NCCL_ID_FILE"), "rb");
+        if (!f || fread(id, 1, 128, f) != 128) { printf("ERROR: cannot read the ncclUniqueId file\n"); return EXIT_FAILURE; }
+        fclose(f);
+        opt.nccl_unique_id = id;
+        prfdd_set_device(opt.proc_id % prfdd_device_count());
+    }
+    else
+    {
+        printf("Running with:\n- Mode: 'CUDA'\n- Device id: 0\n\n"); // poisson.cpp:126-139
+        prfdd_set_device(0);
+    }
+    prfdd_solver *s = nullptr;
+    int rc = prfdd_solver_create(&s, argv[1], &opt, nullptr);
+    if (rc) { printf("ERROR: %s\n", prfdd_error_string(rc)); return EXIT_FAILURE; }
+    prfdd_solver_setup_problem(s, 4);
+    int iters = 0, hl = 0;
+    std::vector<double> hist(2048);
+    rc = prfdd_solver_solve(s, solver_id, &iters, hist.data(), (int)hist.size(), &hl);
+    if (rc) { printf("ERROR: %s\n", prfdd_error_string(rc)); return EXIT_FAILURE; }
+    if (opt.proc_id == 0)
+    {
+        printf("\nRun info:\n-------------------------------------------------------------------------\n");
+        printf("Number of dimensions: %lld\n", prfdd_solver_query(s, PRFDD_Q_DIM));
+        printf("Total number of elements: %lld\n", prfdd_solver_query(s, PRFDD_Q_NUM_TOTAL_ELEMENTS));
+        printf("Polynomial degree: %d\n", opt.poly_degree);
+        printf("Function ID: %d\n", 4);
+        printf("Subdomain overlap: %d\n", opt.subdomain_overlap);
+        printf("Superdomain overlap: %d\n", opt.superdomain_overlap);
+        printf("Solver data precision: %s\n", "double");
+        printf("Solver tolerance: %g\n", opt.outer_tolerance);
+        printf("Solver type: \"%s\"\n", (solver_id == 0) ? "FCG" : "GMRES");
+        printf("Preconditioner data precision: %s\n", "double");
+        printf("Preconditioner tolerance: %g\n", opt.inner_tolerance);
+        printf("Preconditioner type: \"%s\"\n", (opt.preconditioner_type == 0) ? "FCG" : "GMRES");
+        printf("Iterations: %d\n", iters);
+    }
+    prfdd_solver_destroy(s);
+    return EXIT_SUCCESS;
+}
