@@ -490,7 +490,7 @@ struct DeviceCSR
         col.copyFrom(A.col.data(), nnz * sizeof(int));
         val.copyFrom(A.val.data(), nnz * sizeof(double));
         const double avg = (double)nnz / std::max(num_rows, 1);
-        tpr = avg <= 2.5 ? 1 : avg <= 6 ? 2 : avg <= 14 ? 4 : avg <= 40 ? 8 : avg <= 100 ? 16 : 32;
+        tpr = avg <= 10 ? 1 : avg <= 18 ? 2 : avg <= 44 ? 4 : avg <= 60 ? 8 : 16; // measured on B200, profiles/r1_spmv_tpr.txt
     }
 };
 

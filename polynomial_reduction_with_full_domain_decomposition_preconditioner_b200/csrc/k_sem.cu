@@ -13,6 +13,7 @@
 //     after unrolling => constant-bank operands of DFMA, no load instruction at all).
 // Several elements share a CTA so that small degrees still fill warps.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace prfdd
 {
@@ -34,8 +35,8 @@ constexpr int epb3d()
     return (N * N >= 128) ? 1 : (128 / (N * N));
 }
 
-template <int N, int EPB>
-__global__ void __launch_bounds__(N *N *EPB) k_ax3d(double *__restrict__ Au, const double *__restrict__ u, const G6 G, const DParam<N> Dc, const double *__restrict__ Dg, long long first_point, int num_elems)
+template <int N, int EPB, int MINB>
+__global__ void __launch_bounds__(N *N *EPB, MINB) k_ax3d(double *__restrict__ Au, const double *__restrict__ u, const G6 G, const DParam<N> Dc, const double *__restrict__ Dg, long long first_point, int num_elems)
 {
     constexpr int N2 = N * N, N3 = N * N * N;
     constexpr int LD = N + 1; // padded leading dimension: conflict-free row reads by thread-dependent row
@@ -127,6 +128,114 @@ __global__ void __launch_bounds__(N *N *EPB) k_ax3d(double *__restrict__ Au, con
 #pragma unroll
         for (int k = 0; k < N; k++) Au[base + k * N2] = r_Au[k];
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bulk-async (TMA 1D) variant: ONE element per CTA of N*N threads.  One thread issues seven
+// cp.async.bulk copies (u and the six geometric factors of the element, N^3*8 B each, contiguous) that
+// complete on an mbarrier; with ~7 CTAs resident per SM the HBM latency of one element's 7*N^3*8 bytes is
+// hidden behind the contractions of the others, and no register is spent on prefetching G.  The (i,j)
+// slices of u are read straight out of the staged copy (no per-slice store + barrier); G.Du slices are
+// double-buffered so one __syncthreads per k suffices.
+// Requires N^3*8 and the element's byte offset to be multiples of 16.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int N, int MINB>
+__global__ void __launch_bounds__(N *N, MINB) k_ax3d_bulk(double *__restrict__ Au, const double *__restrict__ u, const G6 G, const DParam<N> Dc, const double *__restrict__ Dg, long long first_point, int num_elems)
+{
+    constexpr int N2 = N * N, N3 = N * N * N;
+    constexpr int LD = N + 1;
+    __shared__ __align__(128) double stage[7][N3]; // 0: u, 1..6: G11,G22,G33,G12,G13,G23
+    __shared__ __align__(16) double s_gr[2][N2];
+    __shared__ __align__(16) double s_gs[2][N2];
+    __shared__ double s_D[N * LD];
+    __shared__ __align__(8) unsigned long long bar;
+
+    const int ij = threadIdx.x;
+    const int j = ij / N;
+    const int i = ij - j * N;
+    const long long e = blockIdx.x;
+    const long long ebase = first_point + e * N3;
+    (void)num_elems;
+
+    if (ij == 0)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (ij == 0)
+    {
+        constexpr uint32_t bytes = N3 * 8;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(7u * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&stage[0][0])), "l"(u + ebase), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&stage[1 + c][0])), "l"(G.g[c] + ebase), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
+    }
+    // overlap with the copies: derivative matrix into shared memory, thread-dependent rows into registers
+    for (int t = ij; t < N2; t += N2) s_D[(t / N) * LD + (t % N)] = Dg[t];
+    __syncthreads();
+    double Di[N], Dj[N], Dti[N], Dtj[N];
+#pragma unroll
+    for (int m = 0; m < N; m++)
+    {
+        Di[m] = s_D[i * LD + m];
+        Dj[m] = s_D[j * LD + m];
+        Dti[m] = s_D[m * LD + i];
+        Dtj[m] = s_D[m * LD + j];
+    }
+    // wait for the bytes
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+    }
+
+    double r_u[N], r_Au[N];
+#pragma unroll
+    for (int k = 0; k < N; k++)
+    {
+        r_u[k] = stage[0][k * N2 + ij];
+        r_Au[k] = 0.0;
+    }
+
+#pragma unroll
+    for (int k = 0; k < N; k++)
+    {
+        const double *uk = &stage[0][k * N2];
+        double ur = 0.0, us = 0.0, ut = 0.0;
+#pragma unroll
+        for (int m = 0; m < N; m++)
+        {
+            ur += Di[m] * uk[j * N + m];
+            us += Dj[m] * uk[m * N + i];
+            ut += Dc.v[k * N + m] * r_u[m];
+        }
+        const int p = k * N2 + ij;
+        const double g0 = stage[1][p], g1 = stage[2][p], g2 = stage[3][p], g3 = stage[4][p], g4 = stage[5][p], g5 = stage[6][p];
+        const double gr = g0 * ur + g3 * us + g4 * ut;
+        const double gs = g3 * ur + g1 * us + g5 * ut;
+        const double gt = g4 * ur + g5 * us + g2 * ut;
+        const int b = k & 1;
+        s_gr[b][ij] = gr;
+        s_gs[b][ij] = gs;
+        __syncthreads();
+        double a = 0.0, c2 = 0.0;
+#pragma unroll
+        for (int m = 0; m < N; m++)
+        {
+            a += Dti[m] * s_gr[b][j * N + m];
+            c2 += Dtj[m] * s_gs[b][m * N + i];
+        }
+        r_Au[k] += a + c2;
+#pragma unroll
+        for (int m = 0; m < N; m++) r_Au[m] += Dc.v[k * N + m] * gt;
+    }
+
+#pragma unroll
+    for (int k = 0; k < N; k++) Au[ebase + k * N2 + ij] = r_Au[k];
 }
 
 // large degrees (n > 10): D stays in shared memory, everything else identical
@@ -254,8 +363,19 @@ static int launch_ax3d(double *Au, const double *u, const G6 &G, const double *D
         constexpr int EPB = epb3d<N>();
         DParam<N> Dc;
         for (int t = 0; t < N * N; t++) Dc.v[t] = D_host[t];
+        if constexpr (N == 6 || N == 8)
+        {
+            // bulk-async variant: needs 16-byte aligned element blocks (static shared memory: n <= 8)
+            static const bool no_bulk = getenv("PRFDD_AX_NO_BULK") != nullptr;
+            if (!no_bulk && first_point % 2 == 0)
+            {
+                constexpr int MINB = (N == 6) ? 10 : 6;
+                k_ax3d_bulk<N, MINB><<<num_elems, N * N, 0, st>>>(Au, u, G, Dc, D_dev, first_point, num_elems);
+                return launched();
+            }
+        }
         int grid = (num_elems + EPB - 1) / EPB;
-        k_ax3d<N, EPB><<<grid, N * N * EPB, 0, st>>>(Au, u, G, Dc, D_dev, first_point, num_elems);
+        k_ax3d<N, EPB, 1><<<grid, N * N * EPB, 0, st>>>(Au, u, G, Dc, D_dev, first_point, num_elems);
     }
     else
     {
