@@ -96,6 +96,8 @@ int prfdd_scatter(double *out, const int *node_of_point, const double *nodes, co
  * domain.tpp:590-594; idx lists are strictly increasing per peer so the add needs no atomics) */
 int prfdd_halo_pack(double *buf, const double *nodes, const int *idx, int count, prfdd_stream_t stream);
 int prfdd_halo_unpack_add(double *nodes, const double *buf, const int *idx, int count, prfdd_stream_t stream);
+/* dst[idx[i]] = buf[i]: unpack of the tree exchange into the region slots (replaces gslib_gs + H2D, subdomain.tpp:4625-4631) */
+int prfdd_scatter_assign(double *dst, const double *buf, const int *idx, int count, prfdd_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * CSR SpMV (csr_matrix.okl, AMG/csr_matrix.cpp:126-133 cusparseSpMV)

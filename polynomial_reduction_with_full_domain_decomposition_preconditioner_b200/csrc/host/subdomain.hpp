@@ -39,6 +39,7 @@
 #include "math.hpp"
 #include "special_functions.hpp"
 #include "amg.hpp"
+#include "region_helpers.hpp"
 #include "../../../include/prfdd_b200.h"
 
 template <typename DType>
@@ -110,6 +111,21 @@ class Subdomain
     int num_superdomain_elems = 0;
     int num_superdomain_extended_elems = 0;
     Stiffness_Operator<DType> superdomain_operator;
+    std::vector<Element<DType>> superdomain_region;
+
+    // multi-rank bookkeeping (subdomain_multi.hpp)
+    std::vector<int> proc_count, proc_offset;
+    int num_total_elements = 0;
+    int num_comp_levels = 1;
+    std::vector<long long> dof_num_coarse; // global N = 1 dof of every (element, vertex)
+    std::vector<int> dof_marker, dof_sup;
+    std::map<std::pair<int, int>, std::vector<DType>> J_cf_fem; // hat-function interpolation for hanging nodes (tpp:2754-2783)
+    struct TreeExchange
+    {
+        std::vector<int> peers, send_count, recv_count, send_offset, recv_offset;
+        int send_total = 0, recv_total = 0, coarse_per_rank = 0;
+        memory send_idx, recv_idx, send_buf, recv_buf, coarse_all, coarse_dofs, level_buf;
+    } tree;
 
     // Interface assembly
     int num_interface_dofs = 0;
@@ -149,6 +165,16 @@ class Subdomain
     double *ks_ptr(size_t off) const { return reinterpret_cast<double *>(reinterpret_cast<char *>(kstate.ptr()) + off); }
 
     void build_single_rank(std::map<int, std::unique_ptr<Domain<DType>>> &domains);
+    void build_multi_rank(std::map<int, std::unique_ptr<Domain<DType>>> &domains);
+    void build_region_Q(std::vector<Element<DType>> &region, CSR_Matrix<DType> &Q);
+    void build_superdomain(amg::Hierarchy &H, const std::vector<int> &sub_ids, const std::vector<int> &sup_ids, const std::unordered_set<long long> &interface_glo_num,
+                           const std::vector<long long> &glo_num_coarse, int num_coarse_dofs);
+    void build_interface(const std::vector<int> &sub_ids, const std::vector<int> &sup_ids, const std::vector<int> &subdomain_partition, int n_interface);
+    void setup_tree_exchange();
+    void tree_operator_multi(const memory &Tu, const memory &u);
+    void q1_element_matrix(const DType *const g[NUM_GEOM_FACTS], std::vector<DType> &Ae);
+    std::pair<std::vector<int>, std::vector<int>> matching(const Element<DType> &ei, const Element<DType> &ej, int kind, int idx);
+    int min_degree_edge_neighbor(const std::vector<Element<DType>> &region, const Element<DType> &el, int eid);
     void assemble_low_order_fem();
     void allocate_solver();
     void ranking(std::vector<DType> &data, int size);
@@ -276,12 +302,31 @@ Subdomain<DType>::Subdomain(std::map<int, std::unique_ptr<Domain<DType>>> &domai
         superdomain_operator.D_hat.push_back(D_hat[l].second);
     }
 
+    // hat-function interpolation between the GLL grids of two levels, for hanging nodes of the low-order FEM
+    // (tpp:2754-2783; r_gll as dgll_ left it)
+    for (int l_f = 0; l_f < num_levels - 1; l_f++)
+        for (int l_c = l_f + 1; l_c < num_levels; l_c++)
+        {
+            const int N_f = poly_degree[l_f], N_c = poly_degree[l_c], n_f = N_f + 1, n_c = N_c + 1;
+            std::vector<DType> &J = J_cf_fem[std::pair<int, int>(N_c, N_f)];
+            J.assign(n_c * n_f, 0.0);
+            J[0] = 1.0;
+            for (int i = 1; i < N_f; i++)
+                for (int j = 0; j < N_c; j++)
+                    if ((r_gll[l_c][j] <= r_gll[l_f][i]) and (r_gll[l_f][i] <= r_gll[l_c][j + 1]))
+                    {
+                        J[i * n_c + (j + 0)] = (r_gll[l_c][j + 1] - r_gll[l_f][i]) / (r_gll[l_c][j + 1] - r_gll[l_c][j]);
+                        J[i * n_c + (j + 1)] = (r_gll[l_f][i + 0] - r_gll[l_c][j]) / (r_gll[l_c][j + 1] - r_gll[l_c][j]);
+                    }
+            J[(n_f - 1) * n_c + (n_c - 1)] = 1.0;
+        }
+
     dev::check_rc(prfdd_reduce_ws_create(&ws), "prfdd_reduce_ws_create");
 
     if (num_procs == 1)
         build_single_rank(domains);
     else
-        throw std::runtime_error("Subdomain: the multi-rank PR-FDD setup is not available in this build (num_procs > 1 runs with use_preconditioner = 0)");
+        build_multi_rank(domains);
 
     allocate_solver();
 }
@@ -592,32 +637,144 @@ void Subdomain<DType>::assemble_low_order_fem()
                     }
                 }
         }
-        // scatter J_e^T A_e J_e (J_e is a selection for a conforming element, tpp:3287-3297) to the dofs (tpp:3385-3403)
-        for (int a = 0; a < npts; a++)
-        {
-            const long long ra = elem_i.dof_num[a];
-            if (ra <= 0) continue;
+        // does any edge / face neighbour in the region have a lower degree? (hanging nodes on this element)
+        bool conforming = true;
+        for (auto &c : elem_i.edge_conn)
+            for (int j : c) conforming = conforming && !(subdomain_region[j].poly_degree < N_i);
+        for (auto &c : elem_i.face_conn)
+            for (int j : c) conforming = conforming && !(subdomain_region[j].poly_degree < N_i);
+        auto slot_target = [&](int a, int s) {
             const int ia = a % n_i, ja = (a / n_i) % n_i, ka = a / (n_i * n_i);
-            for (int s = 0; s < nslots; s++)
+            const int ib = ia + (s % 3) - 1, jb = ja + ((s / 3) % 3) - 1, kb = ka + (dim == 3 ? (s / 9) - 1 : 0);
+            return ib + jb * n_i + kb * n_i * n_i;
+        };
+        if (conforming)
+        {
+            // J_e is a selection (tpp:3287-3297): scatter A_e to the dofs (tpp:3385-3403)
+            for (int a = 0; a < npts; a++)
             {
-                if (!touched[(size_t)a * nslots + s]) continue;
-                const DType val = Ae[(size_t)a * nslots + s];
-                if (!(std::abs(val) > epsilon)) continue;
-                const int ib = ia + (s % 3) - 1, jb = ja + ((s / 3) % 3) - 1, kb = ka + (dim == 3 ? (s / 9) - 1 : 0);
-                const int b = ib + jb * n_i + kb * n_i * n_i;
-                const long long cb = elem_i.dof_num[b];
-                if (cb <= 0) continue;
-                rows[ra - 1].push_back({(int)(cb - 1), val});
+                const long long ra = elem_i.dof_num[a];
+                if (ra <= 0) continue;
+                for (int s = 0; s < nslots; s++)
+                {
+                    if (!touched[(size_t)a * nslots + s]) continue;
+                    const DType val = Ae[(size_t)a * nslots + s];
+                    if (!(std::abs(val) > epsilon)) continue;
+                    const long long cb = elem_i.dof_num[slot_target(a, s)];
+                    if (cb <= 0) continue;
+                    rows[ra - 1].push_back({(int)(cb - 1), val});
+                }
+            }
+            continue;
+        }
+        // hanging nodes: columns of J_e = own points with glo_num > 0, then the coarse neighbours' edge / face interiors
+        // (tpp:3130-3355); A_sub_fem += J_e^T A_e J_e
+        {
+            using namespace prfdd_multi;
+            const int num_edges = (dim == 2) ? 4 : 12, num_faces = (dim == 2) ? 0 : 6;
+            int rank = 1;
+            std::vector<std::pair<int, long long>> vert(npts);
+            for (int v = 0; v < npts; v++) vert[v] = {elem_i.glo_num[v] > 0 ? rank++ : 0, elem_i.dof_num[v]};
+            std::vector<std::vector<int>> edge_pts(num_edges), face_pts(num_faces);
+            std::vector<std::vector<std::pair<int, long long>>> edge_cols(num_edges), face_cols(num_faces);
+            for (int q = 0; q < num_edges; q++)
+            {
+                const int e_j = min_degree_edge_neighbor(subdomain_region, elem_i, q);
+                if (e_j < 0) continue;
+                const Element<DType> &ej = subdomain_region[e_j];
+                const int n_j = ej.poly_degree + 1;
+                auto m = matching(elem_i, ej, 0, q);
+                edge_pts[q] = m.first;
+                edge_cols[q].resize(n_j);
+                edge_cols[q][0] = vert[m.first[0]];
+                edge_cols[q][n_j - 1] = vert[m.first[n_i - 1]];
+                for (int k = 1; k < n_j - 1; k++) edge_cols[q][k] = {rank++, ej.dof_num[m.second[k]]};
+            }
+            for (int q = 0; q < num_faces; q++)
+                for (int e_j : elem_i.face_conn[q])
+                {
+                    const Element<DType> &ej = subdomain_region[e_j];
+                    const int n_j = ej.poly_degree + 1;
+                    if (N_i <= ej.poly_degree) continue;
+                    auto m = matching(elem_i, ej, 1, q);
+                    face_pts[q] = m.first;
+                    auto &lst = face_cols[q];
+                    lst.assign(n_j * n_j, {0, 0});
+                    lst[0] = vert[m.first[0]];
+                    lst[n_j - 1] = vert[m.first[n_i - 1]];
+                    lst[(n_j - 1) * n_j] = vert[m.first[(n_i - 1) * n_i]];
+                    lst[n_j * n_j - 1] = vert[m.first[n_i * n_i - 1]];
+                    const int *fe = FACE_EDGES[q];
+                    for (int k = 1; k < n_j - 1; k++)
+                    {
+                        lst[k] = edge_cols[fe[0]][k];
+                        lst[k + (n_j - 1) * n_j] = edge_cols[fe[1]][k];
+                        lst[k * n_j] = edge_cols[fe[2]][k];
+                        lst[(n_j - 1) + k * n_j] = edge_cols[fe[3]][k];
+                    }
+                    for (int b = 1; b < n_j - 1; b++)
+                        for (int a = 1; a < n_j - 1; a++) lst[a + b * n_j] = {rank++, ej.dof_num[m.second[a + b * n_j]]};
+                }
+            const int ncols = rank - 1;
+            std::vector<std::vector<std::pair<int, DType>>> Je(npts);
+            std::vector<long long> dcol(ncols, 0);
+            for (int v = 0; v < npts; v++)
+                if (vert[v].first > 0) { Je[v].push_back({vert[v].first - 1, 1.0}); dcol[vert[v].first - 1] = vert[v].second; }
+            for (int q = 0; q < num_edges; q++)
+            {
+                if (edge_cols[q].empty()) continue;
+                const int n_j = (int)edge_cols[q].size();
+                const std::vector<DType> &Jf = J_cf_fem[std::pair<int, int>(n_j - 1, N_i)];
+                for (auto &pr : edge_cols[q]) dcol[pr.first - 1] = pr.second;
+                for (int i = 1; i < n_i - 1; i++)
+                    for (int j = 0; j < n_j; j++)
+                        if (std::abs(Jf[i * n_j + j]) > epsilon) Je[edge_pts[q][i]].push_back({edge_cols[q][j].first - 1, Jf[i * n_j + j]});
+            }
+            for (int q = 0; q < num_faces; q++)
+            {
+                if (face_cols[q].empty()) continue;
+                const int n_j = (int)std::lround(std::sqrt((double)face_cols[q].size()));
+                const std::vector<DType> &Jf = J_cf_fem[std::pair<int, int>(n_j - 1, N_i)];
+                for (auto &pr : face_cols[q]) dcol[pr.first - 1] = pr.second;
+                for (int j = 1; j < n_i - 1; j++)
+                    for (int i = 1; i < n_i - 1; i++)
+                        for (int qq = 0; qq < n_j; qq++)
+                            for (int pp = 0; pp < n_j; pp++)
+                            {
+                                const DType val = Jf[i * n_j + pp] * Jf[j * n_j + qq];
+                                if (std::abs(val) > epsilon) Je[face_pts[q][i + j * n_i]].push_back({face_cols[q][pp + qq * n_j].first - 1, val});
+                            }
+            }
+            std::vector<DType> acc((size_t)ncols * ncols, 0.0);
+            for (int a = 0; a < npts; a++)
+                for (int s = 0; s < nslots; s++)
+                {
+                    if (!touched[(size_t)a * nslots + s]) continue;
+                    const DType val = Ae[(size_t)a * nslots + s];
+                    const int b = slot_target(a, s);
+                    for (auto &ca : Je[a])
+                        for (auto &cb : Je[b]) acc[(size_t)ca.first * ncols + cb.first] += ca.second * val * cb.second;
+                }
+            for (int ca = 0; ca < ncols; ca++)
+            {
+                if (dcol[ca] <= 0) continue;
+                for (int cb = 0; cb < ncols; cb++)
+                {
+                    const DType val = acc[(size_t)ca * ncols + cb];
+                    if (std::abs(val) > epsilon && dcol[cb] > 0) rows[dcol[ca] - 1].push_back({(int)(dcol[cb] - 1), val});
+                }
             }
         }
     }
 
-    // A_sub_fem -> A_fem through the interface numbering (identity for one rank, tpp:3414-3472)
-    amg::HostCSR &A = A_fem_hst;
-    A.num_rows = A.num_cols = num_dofs;
-    A.ptr.assign(num_dofs + 1, 0);
-    A.col.clear();
-    A.val.clear();
+    // A_sub_fem rows -> composite A_fem through the interface numbering (tpp:3414-3472)
+    const int ne = subdomain_operator.num_extended_dofs;
+    std::vector<int> m(ne + superdomain_operator.num_extended_dofs);
+    if (interface_is_identity)
+        for (size_t i = 0; i < m.size(); i++) m[i] = (int)i;
+    else
+        for (size_t i = 0; i < m.size(); i++) m[i] = Q_int.col_hst[Q_int.ptr_hst[i]];
+    std::vector<std::tuple<int, int, double>> coo;
     for (int i = 0; i < subdomain_operator.num_dofs; i++)
     {
         auto &row = rows[i];
@@ -625,16 +782,19 @@ void Subdomain<DType>::assemble_low_order_fem()
         for (size_t k = 0; k < row.size(); k++)
         {
             if (k > 0 && row[k].first == row[k - 1].first)
-                A.val.back() += row[k].second;
+                std::get<2>(coo.back()) += row[k].second;
             else
-            {
-                A.col.push_back(row[k].first);
-                A.val.push_back(row[k].second);
-            }
+                coo.emplace_back(m[i], m[row[k].first], row[k].second);
         }
-        A.ptr[i + 1] = (int)A.col.size();
         std::vector<std::pair<int, DType>>().swap(row);
     }
+    if (superdomain_operator.num_dofs > 0)
+    {
+        auto &As = superdomain_operator.A;
+        for (int i = num_interface_dofs; i < superdomain_operator.num_dofs; i++)
+            for (int k = As.ptr_hst[i]; k < As.ptr_hst[i + 1]; k++) coo.emplace_back(m[ne + i], m[ne + As.col_hst[k]], As.val_hst[k]);
+    }
+    A_fem_hst = prfdd_multi::csr_from_coo(num_dofs, num_dofs, coo);
 }
 
 template <typename DType>
@@ -779,7 +939,8 @@ void Subdomain<DType>::tree_operator(const memory &Tu, const memory &u)
         timer.stop("subdomain.tree_construction.gpu_to_gpu");
         return;
     }
-    throw std::runtime_error("tree_operator: multi-rank not available in this build");
+    timer.stop("subdomain.tree_construction.gpu_to_gpu");
+    tree_operator_multi(Tu, u);
 }
 
 template <typename DType>
@@ -1099,3 +1260,5 @@ int Subdomain<DType>::apply(int what, const double *in_host, double *out_host)
     default: return -1;
     }
 }
+
+#include "subdomain_multi.hpp"

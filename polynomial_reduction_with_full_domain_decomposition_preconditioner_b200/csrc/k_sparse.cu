@@ -102,6 +102,12 @@ __global__ void __launch_bounds__(256) k_unpack_add(double *__restrict__ nodes, 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) nodes[idx[i]] += buf[i];
 }
 
+__global__ void __launch_bounds__(256) k_scatter_assign(double *__restrict__ dst, const double *__restrict__ buf, const int *__restrict__ idx, int count)
+{
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) dst[idx[i]] = buf[i];
+}
+
 __global__ void __launch_bounds__(256) k_dense_solve(double *__restrict__ x, const double *__restrict__ Ainv, const double *__restrict__ b, int n)
 {
     extern __shared__ double sb[];
@@ -145,6 +151,13 @@ int prfdd_halo_unpack_add(double *nodes, const double *buf, const int *idx, int 
 {
     if (count <= 0) return 0;
     k_unpack_add<<<stream_grid(count, 256, 1, 8), 256, 0, S(stream)>>>(nodes, buf, idx, count);
+    return launched();
+}
+
+int prfdd_scatter_assign(double *dst, const double *buf, const int *idx, int count, prfdd_stream_t stream)
+{
+    if (count <= 0) return 0;
+    k_scatter_assign<<<stream_grid(count, 256, 1, 8), 256, 0, S(stream)>>>(dst, buf, idx, count);
     return launched();
 }
 

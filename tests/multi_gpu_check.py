@@ -21,8 +21,8 @@ def main():
     ap.add_argument("--pc", type=int, default=0)
     ap.add_argument("--dim", type=int, default=3)
     ap.add_argument("--nel", type=int, default=4)
-    ap.add_argument("--N", type=int, default=5)
-    ap.add_argument("--r", type=int, default=2)
+    ap.add_argument("--degree", dest="N", type=int, default=5)
+    ap.add_argument("--reduction", dest="r", type=int, default=2)
     ap.add_argument("--eps", type=float, default=0.04)
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -45,6 +45,12 @@ def main():
         nit, hist = S.solve(solver_id)
         mine = dict(rank=rank, nit=nit, hist=hist, u=S.get_array("U"), nop=S.get_array("NODE_OF_POINT"), bn=S.get_array("BOUNDARY_NODES"),
                     aw=S.get_array("ASSEMBLED_WEIGHT"), nodes=S.query("NUM_GLOBAL_NODES"))
+        if a.pc and solver_id == 0:
+            mine.update(sub=dict(ids=S.get_array("SUB_ELEMENT_IDS"), deg=S.get_array("SUB_ELEMENT_DEGREE"), dof=S.get_array("SUB_DOF_NUM"),
+                                 qptr=S.get_array("SUB_Q_PTR"), qcol=S.get_array("SUB_Q_COL"), qval=S.get_array("SUB_Q_VAL"),
+                                 sizes=[S.query(k) for k in ("SUB_NUM_POINTS", "SUB_NUM_DOFS", "SUB_NUM_EXTENDED_DOFS", "SUP_NUM_DOFS", "SUP_NUM_EXTENDED_DOFS", "NUM_VALUES", "NUM_DOFS")],
+                                 aptr=S.get_array("A_FEM_PTR"), acol=S.get_array("A_FEM_COL"), aval=S.get_array("A_FEM_VAL"), rows=S.get_array("AMG_LEVEL_ROWS"),
+                                 nw=S.get_array("NORM_WEIGHT"), iw=S.get_array("INNER_WEIGHT")))
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
         if rank == 0:
@@ -66,6 +72,21 @@ def main():
                 assert np.array_equal(g["bn"], R.boundary_nodes), "boundary ids differ on rank %d" % g["rank"]
                 assert np.abs(g["aw"] - R.assembled_weight).max() < 1e-15
                 assert g["nodes"] == W.num_global_nodes()
+            if a.pc and solver_id == 0:
+                import scipy.sparse as sp
+                for g in gathered:
+                    So, sub = Sd.ranks[g["rank"]], g["sub"]
+                    assert np.array_equal(sub["ids"], So.elem_id) and np.array_equal(sub["deg"], So.elem_degree), "region differs on rank %d" % g["rank"]
+                    assert np.array_equal(sub["dof"], So.dof_num), "region dof numbering differs on rank %d" % g["rank"]
+                    assert sub["sizes"] == [So.num_points, So.sub_num_dofs, So.sub_num_extended_dofs, So.sup_num_dofs, So.sup_num_extended_dofs, So.num_values, So.num_dofs], (sub["sizes"], g["rank"])
+                    assert np.array_equal(sub["qptr"], So.Q.ptr) and np.array_equal(sub["qcol"], So.Q.col), "region Q structure differs on rank %d" % g["rank"]
+                    assert np.abs(sub["qval"] - So.Q.val).max() < 1e-14
+                    assert np.array_equal(sub["nw"], So.norm_weight) and np.array_equal(sub["iw"], So.inner_weight)
+                    A = sp.csr_matrix((sub["aval"], sub["acol"], sub["aptr"]), shape=(So.num_dofs, So.num_dofs))
+                    assert (A != 0).nnz == (So.A_fem != 0).nnz, ((A != 0).nnz, (So.A_fem != 0).nnz)
+                    assert abs(A - So.A_fem).max() <= 1e-11 * abs(So.A_fem).max(), abs(A - So.A_fem).max()
+                    assert np.array_equal(sub["rows"], [L.n for L in So.amg.levels]), (sub["rows"], [L.n for L in So.amg.levels])
+                print("per-rank region maps, Q, weights, low-order FEM matrix, AMG level sizes: identical to the oracle on all %d ranks" % world, flush=True)
             tol_it = 0 if a.pc else 2
             assert abs(gathered[0]["nit"] - W.num_iterations) <= tol_it, (gathered[0]["nit"], W.num_iterations)
             m = min(len(W.history), gathered[0]["hist"].size)
