@@ -295,6 +295,17 @@ int prfdd_mesh_generate_box(const char *directory, int dim, const int nel[3], in
                             double eps);
 
 /* ---------------------------------------------------------------------------------------------
+ * halo lists for the process-boundary sum (host logic of Domain::setup_halo; stands where gslib_gs_setup stands,
+ * domain.tpp:283-284).  Input: every rank's boundary node ids (rank p: ids[offsets[p] .. offsets[p+1])).
+ * Output for rank `proc_id`: its peers in ascending rank order, and for every peer the LOCAL indices (positions in this
+ * rank's own id list) of the shared nodes sorted by global id -- both sides of a pair therefore use the same order.
+ * peers/peer_count/peer_offset need num_procs entries, idx needs as many entries as this rank has ids times num_procs
+ * in the worst case; returns the number of peers (<0 on error), *total = entries written to idx.
+ * ------------------------------------------------------------------------------------------- */
+int prfdd_halo_build_lists(int proc_id, int num_procs, const long long *ids, const long long *offsets, int *peers, int *peer_count,
+                           int *peer_offset, int *idx, long long idx_capacity, long long *total);
+
+/* ---------------------------------------------------------------------------------------------
  * AMG setup on the HOST (no device needed): the library's deterministic stand-in for the two
  * HYPRE_BoomerAMGSetup calls of the reference (subdomain.tpp:1851-1858, 3480-3489).  Exposed so the
  * hierarchy (C/F splittings, interpolation, Galerkin operators, Chebyshev data) can be inspected and

@@ -378,29 +378,22 @@ void Domain<DType>::setup_halo()
     for (long long i = 0; i < my_n; i++) mine[1 + i] = boundary_nodes[i];
     comm_world.allgather_host(mine.data(), all.data(), (size_t)(max_n + 1) * sizeof(long long));
 
-    std::unordered_map<long long, int> my_idx;
-    my_idx.reserve((size_t)my_n);
-    for (int i = 0; i < num_bdary_nodes; i++) my_idx[boundary_nodes[i]] = i;
-
-    std::vector<int> idx_all;
+    // flatten to (ids, offsets) and let the shared host routine build the per-peer lists
+    std::vector<long long> ids, offsets(num_procs + 1, 0);
     for (int p = 0; p < num_procs; p++)
     {
-        if (p == proc_id) continue;
         const long long *rec = all.data() + (size_t)p * (max_n + 1);
-        std::vector<std::pair<long long, int>> shared;
-        for (long long i = 0; i < rec[0]; i++)
-        {
-            auto it = my_idx.find(rec[1 + i]);
-            if (it != my_idx.end()) shared.push_back({rec[1 + i], it->second});
-        }
-        if (shared.empty()) continue;
-        std::sort(shared.begin(), shared.end()); // by global id: both sides of the pair use the same order
-        if (p > proc_id && halo.first_higher == (int)halo.peers.size() && (halo.peers.empty() || halo.peers.back() < proc_id)) halo.first_higher = (int)halo.peers.size();
-        halo.peers.push_back(p);
-        halo.offset.push_back((int)idx_all.size());
-        halo.count.push_back((int)shared.size());
-        for (auto &s : shared) idx_all.push_back(s.second);
+        offsets[p + 1] = offsets[p] + rec[0];
+        ids.insert(ids.end(), rec + 1, rec + 1 + rec[0]);
     }
+    std::vector<int> peers(num_procs), pcount(num_procs), poffset(num_procs), idx_all((size_t)std::max<long long>(my_n, 1) * num_procs);
+    long long total = 0;
+    int np = prfdd_halo_build_lists(proc_id, num_procs, ids.data(), offsets.data(), peers.data(), pcount.data(), poffset.data(), idx_all.data(), (long long)idx_all.size(), &total);
+    if (np < 0) throw std::runtime_error("Domain::setup_halo: prfdd_halo_build_lists failed");
+    halo.peers.assign(peers.begin(), peers.begin() + np);
+    halo.count.assign(pcount.begin(), pcount.begin() + np);
+    halo.offset.assign(poffset.begin(), poffset.begin() + np);
+    idx_all.resize(total);
     halo.first_higher = 0;
     while (halo.first_higher < (int)halo.peers.size() && halo.peers[halo.first_higher] < proc_id) halo.first_higher++;
     halo.total = (int)idx_all.size();

@@ -2,7 +2,10 @@
 // C ABI (version, device selection, buffers).
 #include "config.hpp"
 #include "../../../include/prfdd_b200.h"
+#include <algorithm>
 #include <string>
+#include <unordered_map>
+#include <vector>
 
 namespace prfdd_host
 {
@@ -34,6 +37,35 @@ const char *prfdd_error_string(int code)
     case -7: return "row_end < row_start";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown prfdd error";
     }
+}
+
+int prfdd_halo_build_lists(int me, int nprocs, const long long *ids, const long long *offsets, int *peers, int *peer_count, int *peer_offset, int *idx,
+                           long long idx_capacity, long long *total)
+{
+    std::unordered_map<long long, int> mine;
+    for (long long i = offsets[me]; i < offsets[me + 1]; i++) mine[ids[i]] = (int)(i - offsets[me]);
+    int np = 0;
+    long long n = 0;
+    for (int p = 0; p < nprocs; p++)
+    {
+        if (p == me) continue;
+        std::vector<std::pair<long long, int>> shared;
+        for (long long i = offsets[p]; i < offsets[p + 1]; i++)
+        {
+            auto it = mine.find(ids[i]);
+            if (it != mine.end()) shared.push_back({ids[i], it->second});
+        }
+        if (shared.empty()) continue;
+        std::sort(shared.begin(), shared.end());
+        if (n + (long long)shared.size() > idx_capacity) return -8;
+        peers[np] = p;
+        peer_offset[np] = (int)n;
+        peer_count[np] = (int)shared.size();
+        for (auto &s : shared) idx[n++] = s.second;
+        np++;
+    }
+    *total = n;
+    return np;
 }
 
 int prfdd_device_count(void)
