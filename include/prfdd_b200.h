@@ -372,6 +372,11 @@ long long prfdd_solver_query(prfdd_solver *s, int what);
 long long prfdd_solver_get_array(prfdd_solver *s, int what, void *dst, long long capacity_bytes);
 /* one application of a building block on host buffers, for parity tests */
 int prfdd_solver_apply(prfdd_solver *s, int what, const double *in_host, double *out_host);
+/* live timing of the dominant kernel of the V-cycle for bench.py's roofline: `reps` back-to-back launches of the fused
+ * Chebyshev SpMV step, alternating between AMG levels 0 and 1 (so that no launch finds its matrix in L2), bracketed by CUDA
+ * events on the solver's stream.  out[0] = average ms per launch, out[1] = average algorithmic bytes per launch
+ * (12*nnz + 4*(rows+1) + 5*8*rows), out[2] = rows of level 0, out[3] = nnz of level 0, out[4] = rows of level 1, out[5] = nnz of level 1 */
+int prfdd_solver_time_spmv(prfdd_solver *s, int reps, double out[6]);
 /* timer report (Timer keys of timer.tpp / poisson.cpp:253-401): seconds for `key`, <0 if unknown */
 double prfdd_solver_timer_total(prfdd_solver *s, const char *key);
 

@@ -21,6 +21,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <numeric>
 #include <vector>
 #include "config.hpp"
@@ -599,10 +601,6 @@ class Hierarchy
                 dev::check_rc(prfdd_csr_multiply(Lc.f.as<double>(), L.dR.ptr.as<int>(), L.dR.col.as<int>(), L.dR.val.as<double>(), L.v.as<double>(), Lc.n, L.dR.tpr, st), "restrict");
             }
             Level &last = levels[nl - 1];
-            if (nl == 1 && iter > 0)
-            {
-                // single level: every cycle is the exact solve of the same right-hand side
-            }
             dev::check_rc(prfdd_dense_solve(last.u.as<double>(), Ainv.as<double>(), last.f.as<double>(), last.n, st), "dense_solve");
             for (int l = nl - 1; l > 0; l--)
             {

@@ -225,12 +225,20 @@ int prfdd_solver_solve_host(prfdd_solver *s, int solver_id, const double *f_host
 {
     return guarded(s, [&]() {
         const size_t bytes = sizeof(double) * (size_t)s->domain->num_local_points;
-        memcpy(s->pin_in, f_host, bytes);
-        dev::check(cudaMemcpyAsync(s->f.ptr(), s->pin_in, bytes, cudaMemcpyHostToDevice, s->stream), "solve_host/h2d");
+        // page-locked caller buffers are used directly; pageable ones are staged through the solver's pinned buffers
+        auto pinned = [](const void *p) {
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+            return a.type == cudaMemoryTypeHost;
+        };
+        const void *src = f_host;
+        if (!pinned(f_host)) { memcpy(s->pin_in, f_host, bytes); src = s->pin_in; }
+        dev::check(cudaMemcpyAsync(s->f.ptr(), src, bytes, cudaMemcpyHostToDevice, s->stream), "solve_host/h2d");
         int rc = do_solve(s, solver_id, num_iterations, history, history_cap, history_len);
-        dev::check(cudaMemcpyAsync(s->pin_out, s->u.ptr(), bytes, cudaMemcpyDeviceToHost, s->stream), "solve_host/d2h");
+        const bool out_pinned = pinned(u_host);
+        dev::check(cudaMemcpyAsync(out_pinned ? (void *)u_host : (void *)s->pin_out, s->u.ptr(), bytes, cudaMemcpyDeviceToHost, s->stream), "solve_host/d2h");
         device.finish();
-        memcpy(u_host, s->pin_out, bytes);
+        if (!out_pinned) memcpy(u_host, s->pin_out, bytes);
         return rc;
     });
 }
@@ -308,6 +316,11 @@ int prfdd_solver_apply(prfdd_solver *s, int what, const double *in_host, double 
         if (!s->subdomain) return -1;
         return s->subdomain->apply(what, in_host, out_host);
     });
+}
+
+int prfdd_solver_time_spmv(prfdd_solver *s, int reps, double out[6])
+{
+    return guarded(s, [&]() { return s->subdomain ? s->subdomain->time_spmv(reps, out) : -1; });
 }
 
 // ---- host-only AMG setup handle ------------------------------------------------------------

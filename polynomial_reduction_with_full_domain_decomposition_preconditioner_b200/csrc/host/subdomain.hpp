@@ -228,6 +228,7 @@ class Subdomain
     long long query(int what);
     long long get_array(int what, void *dst, long long cap);
     int apply(int what, const double *in_host, double *out_host);
+    int time_spmv(int reps, double out[6]);
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1259,6 +1260,44 @@ int Subdomain<DType>::apply(int what, const double *in_host, double *out_host)
     }
     default: return -1;
     }
+}
+
+template <typename DType>
+int Subdomain<DType>::time_spmv(int reps, double out[6])
+{
+    if (amg_fem.num_levels() < 2) return -1;
+    cudaStream_t stream = st();
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    auto step = [&](amg::Level &L) {
+        return prfdd_cheby_step(L.u.as<double>(), L.t1.as<double>(), L.dA.ptr.as<int>(), L.dA.col.as<int>(), L.dA.val.as<double>(), L.t0.as<double>(), L.r.as<double>(), L.ds.as<double>(),
+                                L.coefs[0], 0, 0, L.n, L.dA.tpr, stream);
+    };
+    for (int w = 0; w < 4; w++) { step(amg_fem.levels[0]); step(amg_fem.levels[1]); }
+    cudaEventRecord(e0, stream);
+    for (int r = 0; r < reps; r++)
+    {
+        int rc = step(amg_fem.levels[r & 1]);
+        if (rc) return rc;
+    }
+    cudaEventRecord(e1, stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    double bytes = 0.0;
+    for (int l = 0; l < 2; l++)
+    {
+        const amg::Level &L = amg_fem.levels[l];
+        bytes += 0.5 * (12.0 * L.A.nnz() + 4.0 * (L.n + 1) + 40.0 * L.n);
+        out[2 + 2 * l] = L.n;
+        out[3 + 2 * l] = L.A.nnz();
+    }
+    out[0] = ms / reps;
+    out[1] = bytes;
+    return 0;
 }
 
 #include "subdomain_multi.hpp"
