@@ -6,7 +6,41 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <vector>
+
+// The "Timings:" table of the reference's simulation_data() (poisson.cpp:253-401): same rows, same grouping of the
+// Timer keys.  Printed when PRFDD_TIMINGS is set; phase timing fences the stream around every phase (as the
+// reference's Timer does with device.finish()), so it is off by default and the solve then runs un-fenced.
+static void timings_report(prfdd_solver *s)
+{
+    auto t = [&](const char *key) { const double v = prfdd_solver_timer_total(s, key); return v < 0.0 ? 0.0 : v; };
+    auto sum = [&](std::initializer_list<const char *> keys) { double v = 0.0; for (auto k : keys) v += t(k); return v; };
+    const double inner_products = t("domain.inner_products"), residual_norm = t("domain.residual_norm");
+    const double vector_operations = t("domain.vector_operations"), operator_application = t("domain.operator_application");
+    const double stitching = t("subdomain.stitching");
+    const double subdomain_solver = sum({"subdomain.inner_products", "subdomain.residual_norm", "subdomain.vector_operations",
+        "subdomain.operator_application", "subdomain.preconditioner.assemble_subdomain", "subdomain.preconditioner.assemble_composite",
+        "subdomain.preconditioner.memcpy", "subdomain.preconditioner.vector_operations", "subdomain.preconditioner.down_leg_gpu",
+        "subdomain.preconditioner.coarse_grid_solver", "subdomain.preconditioner.up_leg_gpu",
+        "subdomain.preconditioner.unassemble_subdomain", "subdomain.preconditioner.unassemble_composite"});
+    const double tree_construction = sum({"subdomain.tree_construction.gpu_to_gpu", "subdomain.tree_construction.subdomain",
+        "subdomain.tree_construction.gpu_to_cpu", "subdomain.tree_construction.assemble_coarse", "subdomain.tree_construction.superdomain"});
+    const double tree_exchange = sum({"subdomain.tree_exchange.superdomain", "subdomain.tree_exchange.subdomain", "subdomain.tree_exchange.cpu_to_gpu"});
+    const double total = inner_products + residual_norm + vector_operations + operator_application + tree_construction + tree_exchange +
+                         stitching + subdomain_solver;
+    const double d = total > 0.0 ? total : 1.0;
+    printf("\nTimings:\n-------------------------------------------------------------------------\n");
+    printf("Total                 = %12.08f s ( %6.02f )\n", total, 100.0);
+    printf("Inner products        = %12.08f s ( %6.02f )\n", inner_products, 100.0 * inner_products / d);
+    printf("Residual norm         = %12.08f s ( %6.02f )\n", residual_norm, 100.0 * residual_norm / d);
+    printf("Vector operations     = %12.08f s ( %6.02f )\n", vector_operations, 100.0 * vector_operations / d);
+    printf("Operator application  = %12.08f s ( %6.02f )\n", operator_application, 100.0 * operator_application / d);
+    printf("Tree construction     = %12.08f s ( %6.02f )\n", tree_construction, 100.0 * tree_construction / d);
+    printf("Tree exchange         = %12.08f s ( %6.02f )\n", tree_exchange, 100.0 * tree_exchange / d);
+    printf("Subdomain stitching   = %12.08f s ( %6.02f )\n", stitching, 100.0 * stitching / d);
+    printf("Subdomain solver      = %12.08f s ( %6.02f )\n", subdomain_solver, 100.0 * subdomain_solver / d);
+}
 
 int main(int argc, char *argv[])
 {
@@ -49,6 +83,8 @@ int main(int argc, char *argv[])
     int rc = prfdd_solver_create(&s, argv[1], &opt, nullptr);
     if (rc) { printf("ERROR: %s\n", prfdd_error_string(rc)); return EXIT_FAILURE; }
     prfdd_solver_setup_problem(s, 4);
+    const bool timings = getenv("PRFDD_TIMINGS") != nullptr;
+    if (timings) prfdd_solver_timer_total(s, "__enable__");
     int iters = 0, hl = 0;
     std::vector<double> hist(2048);
     rc = prfdd_solver_solve(s, solver_id, &iters, hist.data(), (int)hist.size(), &hl);
@@ -69,6 +105,7 @@ int main(int argc, char *argv[])
         printf("Preconditioner tolerance: %g\n", opt.inner_tolerance);
         printf("Preconditioner type: \"%s\"\n", (opt.preconditioner_type == 0) ? "FCG" : "GMRES");
         printf("Iterations: %d\n", iters);
+        if (timings) timings_report(s);
     }
     prfdd_solver_destroy(s);
     return EXIT_SUCCESS;

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 
 from oracle import domain as odomain, subdomain as osub  # noqa: E402
 
-CASES = [(2, 4, 4, 3, 0.0), (2, 8, 7, 3, 0.05), (2, 16, 7, 3, 0.0), (3, 3, 4, 3, 0.05), (3, 2, 7, 6, 0.03), (3, 4, 7, 3, 0.0), (3, 3, 2, 1, 0.04), (2, 5, 1, 1, 0.1)]
+CASES = [(2, 4, 4, 3, 0.0), (2, 8, 7, 3, 0.05), (2, 16, 7, 3, 0.0), (3, 3, 4, 3, 0.05), (3, 2, 7, 6, 0.03), (3, 4, 7, 3, 0.0), (3, 3, 2, 1, 0.04), (2, 5, 1, 1, 0.1),
+         (3, 2, 9, 3, 0.03), (3, 2, 15, 7, 0.02), (2, 3, 15, 7, 0.0)]   # configs 4 / 5 degrees: ladders 9/6/3/1 and 15/8/1
 
 
 def _need_gpu():
