@@ -146,22 +146,6 @@ int prfdd_cheby_order1(double *u, const double *r, const double *ds, double c, i
 /* v = f - A u                                    subdomain.tpp:3660-3661 */
 int prfdd_csr_residual(double *v, const int *ptr, const int *col, const double *val, const double *u, const double *f,
                        int num_rows, int threads_per_row, prfdd_stream_t stream);
-/* Streamed variants of the V-cycle's matrix passes for the large AMG levels (same contracts as the functions above).
- * A CTA stages the col/val slice of a block of consecutive rows in shared memory with bulk-async copies, multiplies by the
- * gathered x flat over the block and adds each row's products with `threads_per_row` lanes.  `row_blocks` (device,
- * num_blocks+1 ints) comes from prfdd_csr_row_blocks (host arrays; returns -9 if one row alone exceeds a block: keep the
- * plain kernels for that matrix); `nnz` = ptr[num_rows].  col and val must be 16-byte aligned. */
-int prfdd_csr_row_blocks(const int *ptr_host, int num_rows, int *row_blocks_host, int *num_blocks);
-int prfdd_csr_multiply_stream(double *Au, const int *ptr, const int *col, const double *val, const double *u, const int *row_blocks,
-                              int num_blocks, int nnz, int threads_per_row, prfdd_stream_t stream);
-int prfdd_csr_residual_stream(double *v, const int *ptr, const int *col, const double *val, const double *u, const double *f,
-                              const int *row_blocks, int num_blocks, int nnz, int threads_per_row, prfdd_stream_t stream);
-int prfdd_cheby_residual_stream(double *r, double *t, const int *ptr, const int *col, const double *val, const double *u, const double *f,
-                                const double *ds, double c_hi, const int *row_blocks, int num_blocks, int nnz, int threads_per_row,
-                                prfdd_stream_t stream);
-int prfdd_cheby_step_stream(double *u, double *t_out, const int *ptr, const int *col, const double *val, const double *t_in, const double *r,
-                            const double *ds, double c, int last, int u_is_zero, const int *row_blocks, int num_blocks, int nnz,
-                            int threads_per_row, prfdd_stream_t stream);
 /* x = Ainv b for the coarsest level (dense, row-major n*n); replaces hypre_GaussElimSolve, subdomain.tpp:4080-4088 */
 int prfdd_dense_solve(double *x, const double *Ainv, const double *b, int n, prfdd_stream_t stream);
 

@@ -492,7 +492,7 @@ struct DeviceCSR
         col.copyFrom(A.col.data(), nnz * sizeof(int));
         val.copyFrom(A.val.data(), nnz * sizeof(double));
         const double avg = (double)nnz / std::max(num_rows, 1);
-        tpr = avg <= 10 ? 1 : avg <= 18 ? 2 : avg <= 44 ? 4 : avg <= 60 ? 8 : 16; // measured on B200, profiles/r1_spmv_tpr.txt
+        tpr = avg <= 10 ? 1 : avg <= 18 ? 2 : (avg > 60 && num_rows < 50000) ? 16 : 8; // measured on B200, profiles/r1_spmv_tpr.txt and r1_notes.txt
     }
 };
 

@@ -131,7 +131,7 @@ class CSR_Matrix
         col.copyFrom(col_hst.data(), num_nnz * sizeof(int));
         val.copyFrom(val_hst.data(), num_nnz * sizeof(DType));
         double avg = (double)num_nnz / (double)std::max(num_rows, 1);
-        threads_per_row = avg <= 10 ? 1 : avg <= 18 ? 2 : avg <= 44 ? 4 : avg <= 60 ? 8 : 16; // measured on B200, profiles/r1_spmv_tpr.txt
+        threads_per_row = avg <= 10 ? 1 : avg <= 18 ? 2 : (avg > 60 && num_rows < 50000) ? 16 : 8; // measured on B200, profiles/r1_spmv_tpr.txt and r1_notes.txt
     }
 
     void print(FILE *file_ptr = NULL, int offset = 0)

@@ -93,92 +93,14 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
     }
 }
 
-// flat variant for rows longer than a few entries: a warp owns R consecutive rows, i.e. one contiguous
-// slice of col/val.  Lanes stride FLAT through the slice (fully coalesced, every lane busy whatever
-// the individual row lengths, independent iterations -> many loads in flight), park the products
-// val * x[col] in the warp's shared-memory strip, and 32/R lanes per row then add each row's
-// products in a fixed order.  No CTA-wide barrier; a slice longer than the strip falls back to the
-// sub-warp-per-row walk for that warp.
-constexpr int kFlatCap = 512; // products per warp strip
-
-template <int R, class Epi>
-__global__ void __launch_bounds__(kSpThreads) k_spmv_flat(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, int row_start, int num_rows, Epi epi)
-{
-    constexpr int TPR = 32 / R;
-    __shared__ double sprod[kSpThreads / 32][kFlatCap];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sub = lane / TPR, sl = lane % TPR;
-    double *strip = sprod[warp];
-    const long long rows_per_grid = (long long)gridDim.x * (kSpThreads / 32) * R;
-    for (long long r0 = ((long long)blockIdx.x * (kSpThreads / 32) + warp) * R; r0 < num_rows; r0 += rows_per_grid)
-    {
-        const int pl0 = ptr[row_start + min(r0 + lane, (long long)num_rows)];
-        const int pl1 = ptr[row_start + min(r0 + lane + 1, (long long)num_rows)];
-        const int p_begin = __shfl_sync(0xffffffffu, pl0, 0);
-        const int n = __shfl_sync(0xffffffffu, pl1, R - 1) - p_begin;
-        const int s = __shfl_sync(0xffffffffu, pl0, sub) - p_begin, e = __shfl_sync(0xffffffffu, pl1, sub) - p_begin;
-        double acc = 0.0;
-        if (n <= kFlatCap)
-        {
-            const int *c = col + p_begin;
-            const double *v = val + p_begin;
-            // batches of 8 x 32 entries: all col/val loads of a batch are issued before the first gather, all gathers
-            // before the first store, so one batch costs two memory latencies whatever its size
-            for (int base = 0; base < n; base += 256)
-            {
-                int cc[8];
-                double vv[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-                {
-                    const int k = base + lane + 32 * u;
-                    const bool on = k < n;
-                    cc[u] = on ? c[k] : -1;
-                    vv[u] = on ? v[k] : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) vv[u] *= cc[u] >= 0 ? x[cc[u]] : 0.0;
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-                {
-                    const int k = base + lane + 32 * u;
-                    if (k < n) strip[k] = vv[u];
-                }
-            }
-            __syncwarp();
-            for (int j = s + sl; j < e; j += TPR) acc += strip[j];
-            __syncwarp();
-        }
-        else
-        {
-            for (int j = p_begin + s + sl; j < p_begin + e; j += TPR) acc += val[j] * x[col[j]];
-        }
-#pragma unroll
-        for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, TPR);
-        if (sl == 0 && r0 + sub < num_rows) epi(row_start + (int)(r0 + sub), acc);
-    }
-}
-
-template <int R, class Epi>
-static void launch_flat(const int *ptr, const int *col, const double *val, const double *x, int row_start, int num_rows, cudaStream_t st, Epi epi)
-{
-    const int grid = stream_grid(((long long)num_rows + R - 1) / R * 32, kSpThreads, 1, 16);
-    k_spmv_flat<R><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, epi);
-}
-
-static int spmv_rpg()
-{
-    static const int v = [] { const char *e = getenv("PRFDD_SPMV_RPG"); const int r = e ? atoi(e) : 1; return (r == 2 || r == 4) ? r : 1; }();
-    return v;
-}
-
 template <int TPR, class Epi>
 static void launch_spmv(const int *ptr, const int *col, const double *val, const double *x, int row_start, int num_rows, cudaStream_t st, Epi epi)
 {
-    const int rpg = TPR == 1 ? 1 : spmv_rpg();
-    const int grid = stream_grid((long long)num_rows * TPR / rpg, kSpThreads, 1, 16);
-    if (rpg == 2) k_spmv<TPR, 2><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, epi);
-    else if (rpg == 4) k_spmv<TPR, 4><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, epi);
+    // two rows per sub-warp once the matrix is large enough to fill the machine with half as many warps
+    // (AMG level 1 of the 16^3 N=7 problem, 27 entries/row: 54.9 -> 49.1 us; profiles/r1_notes.txt)
+    const bool two = TPR >= 4 && (long long)num_rows * TPR >= (1ll << 21);
+    const int grid = stream_grid((long long)num_rows * TPR / (two ? 2 : 1), kSpThreads, 1, 16);
+    if (two) k_spmv<TPR, 2><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, epi);
     else k_spmv<TPR, 1><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, epi);
 }
 
@@ -186,153 +108,15 @@ template <class Epi>
 static int spmv(const int *ptr, const int *col, const double *val, const double *x, int row_start, int num_rows, int tpr, cudaStream_t st, Epi epi)
 {
     if (num_rows <= 0) return 0;
-    if (tpr == 0) tpr = 4;
-    if (tpr < 0 && !x) tpr = 1; // no product to form (u = 0 shortcut): the epilogue alone
+    if (tpr <= 0) tpr = 4;
     switch (tpr)
     {
-    case -1: launch_flat<1>(ptr, col, val, x, row_start, num_rows, st, epi); break;
-    case -2: launch_flat<2>(ptr, col, val, x, row_start, num_rows, st, epi); break;
-    case -4: launch_flat<4>(ptr, col, val, x, row_start, num_rows, st, epi); break;
-    case -8: launch_flat<8>(ptr, col, val, x, row_start, num_rows, st, epi); break;
-    case -16: launch_flat<16>(ptr, col, val, x, row_start, num_rows, st, epi); break;
-    case -32: launch_flat<32>(ptr, col, val, x, row_start, num_rows, st, epi); break;
     case 1: launch_spmv<1>(ptr, col, val, x, row_start, num_rows, st, epi); break;
     case 2: launch_spmv<2>(ptr, col, val, x, row_start, num_rows, st, epi); break;
     case 4: launch_spmv<4>(ptr, col, val, x, row_start, num_rows, st, epi); break;
     case 8: launch_spmv<8>(ptr, col, val, x, row_start, num_rows, st, epi); break;
     case 16: launch_spmv<16>(ptr, col, val, x, row_start, num_rows, st, epi); break;
     case 32: launch_spmv<32>(ptr, col, val, x, row_start, num_rows, st, epi); break;
-    default: return -6;
-    }
-    return launched();
-}
-
-// ---------------------------------------------------------------------------------------------
-// streamed SpMV for the large AMG levels: one CTA owns a block of consecutive rows whose entries
-// (<= CH of them) are contiguous in col/val.  One thread moves the block's col and val slices into
-// shared memory with two cp.async.bulk copies completing on an mbarrier (the streaming part of the
-// SpMV is then a deep DMA instead of per-lane loads that wait on each other); every thread then
-// multiplies entries by the gathered x[col] flat over the block (all lanes busy whatever the row
-// lengths, many independent gathers in flight per thread), and sub-warps of TPR lanes add the
-// products of each row from shared memory in a fixed order and run the epilogue.
-// row_blocks[b] .. row_blocks[b+1] are the rows of block b (prfdd_csr_row_blocks builds them).
-// ---------------------------------------------------------------------------------------------
-constexpr int kStThreads = 256;
-constexpr int kStMaxRows = 1024; // rows per block (shared row-pointer slice)
-
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <int CH, int TPR, class Epi>
-__global__ void __launch_bounds__(kStThreads) k_spmv_stream(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, const int *__restrict__ row_blocks, int nnz_total, Epi epi)
-{
-    extern __shared__ __align__(16) unsigned char stream_smem[];
-    double *sval = reinterpret_cast<double *>(stream_smem);
-    int *scol = reinterpret_cast<int *>(stream_smem + sizeof(double) * CH);
-    int *sptr = scol + CH;
-    __shared__ __align__(8) unsigned long long bar;
-
-    const int tid = threadIdx.x;
-    const int r0 = row_blocks[blockIdx.x], r1 = row_blocks[blockIdx.x + 1], nr = r1 - r0;
-    const int p0 = ptr[r0], p1 = ptr[r1];
-    const int a0 = p0 & ~3;                                  // 16-byte aligned start of the col slice
-    const int nb = max(min((p1 + 3) & ~3, nnz_total & ~3) - a0, 0); // entries moved by the bulk copies
-    if (tid == 0)
-    {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (nb > 0)
-        {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar)), "r"(12u * (uint32_t)nb) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(scol)), "l"(col + a0), "r"(4u * (uint32_t)nb), "r"(smem_addr(&bar)) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(sval)), "l"(val + a0), "r"(8u * (uint32_t)nb), "r"(smem_addr(&bar)) : "memory");
-        }
-    }
-    for (int i = tid; i <= nr; i += kStThreads) sptr[i] = ptr[r0 + i] - a0;
-    for (int i = a0 + nb + tid; i < p1; i += kStThreads) // the < 4 entries at the very end of the matrix that no aligned copy covers
-    {
-        scol[i - a0] = col[i];
-        sval[i - a0] = val[i];
-    }
-    __syncthreads();
-    if (nb > 0)
-    {
-        uint32_t done = 0;
-        while (!done)
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_addr(&bar)), "r"(0u) : "memory");
-    }
-    // flat gather-multiply over the block's entries
-    const int lo = p0 - a0, hi = p1 - a0;
-    int i = lo + tid;
-    for (; i + 3 * kStThreads < hi; i += 4 * kStThreads)
-    {
-        const double x0 = x[scol[i]], x1 = x[scol[i + kStThreads]], x2 = x[scol[i + 2 * kStThreads]], x3 = x[scol[i + 3 * kStThreads]];
-        sval[i] *= x0;
-        sval[i + kStThreads] *= x1;
-        sval[i + 2 * kStThreads] *= x2;
-        sval[i + 3 * kStThreads] *= x3;
-    }
-    for (; i < hi; i += kStThreads) sval[i] *= x[scol[i]];
-    __syncthreads();
-    // per-row sums
-    constexpr int RPP = kStThreads / TPR;
-    const int lane = tid % TPR;
-    for (int base = 0; base < nr; base += RPP)
-    {
-        const int rl = base + tid / TPR;
-        const bool valid = rl < nr;
-        const int s = valid ? sptr[rl] : 0, e = valid ? sptr[rl + 1] : 0;
-        double acc = 0.0;
-        for (int j = s + lane; j < e; j += TPR) acc += sval[j];
-#pragma unroll
-        for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, TPR);
-        if (valid && lane == 0) epi(r0 + rl, acc);
-    }
-}
-
-constexpr size_t stream_smem_bytes(int ch) { return (size_t)ch * 12 + (kStMaxRows + 1) * 4; }
-static int stream_chunk()
-{
-    static const int ch = [] { const char *e = getenv("PRFDD_STREAM_CHUNK"); const int v = e ? atoi(e) : 4096; return (v == 1024 || v == 2048) ? v : 4096; }();
-    return ch;
-}
-
-template <int CH, int TPR, class Epi>
-static void launch_stream_ch(const int *ptr, const int *col, const double *val, const double *x, const int *row_blocks, int num_blocks, int nnz_total, cudaStream_t st, Epi epi)
-{
-    auto kern = k_spmv_stream<CH, TPR, Epi>;
-    static bool configured = false; // one per template instance
-    if (!configured)
-    {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(CH));
-        configured = true;
-    }
-    kern<<<num_blocks, kStThreads, stream_smem_bytes(CH), st>>>(ptr, col, val, x, row_blocks, nnz_total, epi);
-}
-
-template <int TPR, class Epi>
-static void launch_stream(const int *ptr, const int *col, const double *val, const double *x, const int *row_blocks, int num_blocks, int nnz_total, cudaStream_t st, Epi epi)
-{
-    switch (stream_chunk())
-    {
-    case 1024: launch_stream_ch<1024, TPR>(ptr, col, val, x, row_blocks, num_blocks, nnz_total, st, epi); break;
-    case 2048: launch_stream_ch<2048, TPR>(ptr, col, val, x, row_blocks, num_blocks, nnz_total, st, epi); break;
-    default: launch_stream_ch<4096, TPR>(ptr, col, val, x, row_blocks, num_blocks, nnz_total, st, epi); break;
-    }
-}
-
-template <class Epi>
-static int spmv_stream(const int *ptr, const int *col, const double *val, const double *x, const int *row_blocks, int num_blocks, int nnz_total, int tpr, cudaStream_t st, Epi epi)
-{
-    if (num_blocks <= 0) return 0;
-    if (((uintptr_t)col & 15) || ((uintptr_t)val & 15)) return -8; // bulk copies need 16-byte aligned arrays
-    switch (tpr)
-    {
-    case 1: launch_stream<1>(ptr, col, val, x, row_blocks, num_blocks, nnz_total, st, epi); break;
-    case 2: launch_stream<2>(ptr, col, val, x, row_blocks, num_blocks, nnz_total, st, epi); break;
-    case 4: launch_stream<4>(ptr, col, val, x, row_blocks, num_blocks, nnz_total, st, epi); break;
-    case 8: launch_stream<8>(ptr, col, val, x, row_blocks, num_blocks, nnz_total, st, epi); break;
-    case 16: launch_stream<16>(ptr, col, val, x, row_blocks, num_blocks, nnz_total, st, epi); break;
-    case 32: launch_stream<32>(ptr, col, val, x, row_blocks, num_blocks, nnz_total, st, epi); break;
     default: return -6;
     }
     return launched();
@@ -488,66 +272,6 @@ int prfdd_cheby_step(double *u, double *t_out, const int *ptr, const int *col, c
         });
     }
     return spmv(ptr, col, val, t_in, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) {
-        const double d = ds[row];
-        t_out[row] = d * (c * r[row] + d * ax);
-    });
-}
-
-// streamed variants (k_spmv_stream) of the V-cycle's matrix passes; same arithmetic per row, the products of a row are
-// added TPR-strided from shared memory
-int prfdd_csr_row_blocks(const int *ptr_host, int num_rows, int *row_blocks, int *num_blocks)
-{
-    // greedy: consecutive rows while the block's entries (plus alignment slack) fit the shared-memory chunk
-    int nb = 0, r = 0;
-    while (r < num_rows)
-    {
-        int e = r;
-        while (e < num_rows && e - r < kStMaxRows && ptr_host[e + 1] - ptr_host[r] <= stream_chunk() - 8) e++;
-        if (e == r) return -9; // a single row does not fit: use the plain kernels for this matrix
-        if (row_blocks) row_blocks[nb] = r;
-        nb++;
-        r = e;
-    }
-    if (row_blocks) row_blocks[nb] = num_rows;
-    *num_blocks = nb;
-    return 0;
-}
-
-int prfdd_csr_multiply_stream(double *Au, const int *ptr, const int *col, const double *val, const double *u, const int *row_blocks, int num_blocks, int nnz, int tpr, prfdd_stream_t stream)
-{
-    return spmv_stream(ptr, col, val, u, row_blocks, num_blocks, nnz, tpr, S(stream), [=] __device__(int row, double ax) { Au[row] = ax; });
-}
-
-int prfdd_csr_residual_stream(double *v, const int *ptr, const int *col, const double *val, const double *u, const double *f, const int *row_blocks, int num_blocks, int nnz, int tpr, prfdd_stream_t stream)
-{
-    return spmv_stream(ptr, col, val, u, row_blocks, num_blocks, nnz, tpr, S(stream), [=] __device__(int row, double ax) { v[row] = f[row] - ax; });
-}
-
-int prfdd_cheby_residual_stream(double *r, double *t, const int *ptr, const int *col, const double *val, const double *u, const double *f, const double *ds, double c_hi, const int *row_blocks, int num_blocks, int nnz, int tpr, prfdd_stream_t stream)
-{
-    return spmv_stream(ptr, col, val, u, row_blocks, num_blocks, nnz, tpr, S(stream), [=] __device__(int row, double ax) {
-        const double d = ds[row];
-        const double rr = d * (f[row] - ax);
-        r[row] = rr;
-        t[row] = d * (c_hi * rr);
-    });
-}
-
-int prfdd_cheby_step_stream(double *u, double *t_out, const int *ptr, const int *col, const double *val, const double *t_in, const double *r, const double *ds, double c, int last, int u_is_zero, const int *row_blocks, int num_blocks, int nnz, int tpr, prfdd_stream_t stream)
-{
-    if (last)
-    {
-        if (u_is_zero)
-            return spmv_stream(ptr, col, val, t_in, row_blocks, num_blocks, nnz, tpr, S(stream), [=] __device__(int row, double ax) {
-                const double d = ds[row];
-                u[row] = d * (c * r[row] + d * ax);
-            });
-        return spmv_stream(ptr, col, val, t_in, row_blocks, num_blocks, nnz, tpr, S(stream), [=] __device__(int row, double ax) {
-            const double d = ds[row];
-            u[row] += d * (c * r[row] + d * ax);
-        });
-    }
-    return spmv_stream(ptr, col, val, t_in, row_blocks, num_blocks, nnz, tpr, S(stream), [=] __device__(int row, double ax) {
         const double d = ds[row];
         t_out[row] = d * (c * r[row] + d * ax);
     });

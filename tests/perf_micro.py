@@ -34,6 +34,22 @@ def timeit(fn, reps=20, warm=3):
     return float(np.median(ts)), float(np.min(ts))
 
 
+def timeit_batch(fn, reps=20, warm=3):
+    """`reps` back-to-back launches between one event pair, no L2 flush: for operands larger than L2 (a flush leaves dirty lines
+    whose write-back is charged to the kernel, and a per-launch event pair adds ~6-10 us); returns (avg, avg)"""
+    with torch.cuda.stream(stream):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        stream.synchronize()
+    t = e0.elapsed_time(e1) / reps
+    return t, t
+
+
 def bench_ax():
     E, n = 4096, 8
     Pn = E * n ** 3

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import polynomial_reduction_with_full_domain_decomposition_preconditioner_b200 as pr  # noqa: E402
 from test_amg_host import product_hierarchy  # noqa: E402
-from perf_micro import timeit, P, L, sh, PEAK  # noqa: E402
+from perf_micro import timeit_batch as timeit, P, L, sh, PEAK  # noqa: E402
 
 
 def tpr_of(A):
