@@ -514,6 +514,12 @@ class Hierarchy
     int cheby_order = 2;
     std::vector<double> Ainv_hst;
     dev::memory Ainv;
+    // Collapsed coarse levels.  Below the first level the V-cycle always starts from a zero guess and the Chebyshev coefficients are
+    // fixed, so the whole sub-cycle from level `collapse_level` down to the coarsest inverse and back is ONE linear map
+    // u = B f.  The levels with a few thousand rows or fewer are launch-latency bound (7 kernels per level, ~3 us each, for a few
+    // KB of data), so B is formed once at set-up (the sub-cycle applied to the unit vectors) and applied as a dense product.
+    int collapse_level = -1;
+    dev::memory Bdense;
 
     int num_levels() const { return (int)levels.size(); }
 
@@ -561,6 +567,38 @@ class Hierarchy
         }
         Ainv = device.malloc<double>(std::max<size_t>(Ainv_hst.size(), 1));
         Ainv.copyFrom(Ainv_hst.data(), Ainv_hst.size() * sizeof(double));
+        static const bool no_collapse = getenv("PRFDD_AMG_NO_COLLAPSE") != nullptr;
+        if (!no_collapse) collapse(2048);
+    }
+
+    void collapse(int max_rows)
+    {
+        using prfdd_host::device;
+        const int nl = num_levels();
+        collapse_level = -1;
+        int lc = -1;
+        for (int l = 1; l < nl - 1; l++)
+            if (levels[l].n <= max_rows) { lc = l; break; }
+        if (lc < 0) return;
+        cudaStream_t st = device.stream;
+        Level &L = levels[lc];
+        const size_t n = (size_t)L.n;
+        dev::memory Bt = device.malloc<double>(n * n); // row i = sub-cycle applied to e_i = column i of B
+        const double one = 1.0;
+        for (size_t i = 0; i < n; i++)
+        {
+            cudaMemsetAsync(L.f.as<double>(), 0, n * sizeof(double), st);
+            cudaMemcpyAsync(L.f.as<double>() + i, &one, sizeof(double), cudaMemcpyHostToDevice, st);
+            cycle_from(lc);
+            cudaMemcpyAsync(Bt.as<double>() + i * n, L.u.as<double>(), n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        }
+        std::vector<double> bt(n * n), b(n * n);
+        Bt.copyTo(bt.data(), n * n * sizeof(double));
+        for (size_t i = 0; i < n; i++)
+            for (size_t j = 0; j < n; j++) b[j * n + i] = bt[i * n + j];
+        Bdense = device.malloc<double>(n * n);
+        Bdense.copyFrom(b.data(), n * n * sizeof(double));
+        collapse_level = lc;
     }
 
     // hypre-style Chebyshev smoothing: r = ds(f - A u); w = c[k-1] r; for p = k-2..0: w = c[p] r + ds A ds w; u += ds w
@@ -585,31 +623,36 @@ class Hierarchy
         }
     }
 
-    // levels[0].f holds the right-hand side; result in levels[0].u   (subdomain.tpp:4012-4139)
-    void vcycle(int num_vcycles)
+    // zero-guess cycle over the levels l0 .. coarsest: levels[l0].f -> levels[l0].u   (subdomain.tpp:4012-4139)
+    void cycle_from(int l0, bool first_guess_is_zero = true)
     {
         cudaStream_t st = prfdd_host::device.stream;
         const int nl = num_levels();
-        for (int iter = 0; iter < num_vcycles; iter++)
+        const int bottom = (collapse_level >= 0 && collapse_level >= l0) ? collapse_level : nl - 1;
+        for (int l = l0; l < bottom; l++)
         {
-            for (int l = 0; l < nl - 1; l++)
-            {
-                Level &L = levels[l];
-                smooth(L, l > 0 || iter == 0);
-                dev::check_rc(prfdd_csr_residual(L.v.as<double>(), L.dA.ptr.as<int>(), L.dA.col.as<int>(), L.dA.val.as<double>(), L.u.as<double>(), L.f.as<double>(), L.n, L.dA.tpr, st), "csr_residual");
-                Level &Lc = levels[l + 1];
-                dev::check_rc(prfdd_csr_multiply(Lc.f.as<double>(), L.dR.ptr.as<int>(), L.dR.col.as<int>(), L.dR.val.as<double>(), L.v.as<double>(), Lc.n, L.dR.tpr, st), "restrict");
-            }
-            Level &last = levels[nl - 1];
-            dev::check_rc(prfdd_dense_solve(last.u.as<double>(), Ainv.as<double>(), last.f.as<double>(), last.n, st), "dense_solve");
-            for (int l = nl - 1; l > 0; l--)
-            {
-                Level &L = levels[l - 1];
-                Level &Lc = levels[l];
-                dev::check_rc(prfdd_csr_matvec(L.u.as<double>(), L.dP.ptr.as<int>(), L.dP.col.as<int>(), L.dP.val.as<double>(), Lc.u.as<double>(), 1.0, 1.0, L.n, L.dP.tpr, st), "prolong");
-                smooth(L, false);
-            }
+            Level &L = levels[l];
+            smooth(L, l > l0 || first_guess_is_zero);
+            dev::check_rc(prfdd_csr_residual(L.v.as<double>(), L.dA.ptr.as<int>(), L.dA.col.as<int>(), L.dA.val.as<double>(), L.u.as<double>(), L.f.as<double>(), L.n, L.dA.tpr, st), "csr_residual");
+            Level &Lc = levels[l + 1];
+            dev::check_rc(prfdd_csr_multiply(Lc.f.as<double>(), L.dR.ptr.as<int>(), L.dR.col.as<int>(), L.dR.val.as<double>(), L.v.as<double>(), Lc.n, L.dR.tpr, st), "restrict");
         }
+        Level &last = levels[bottom];
+        if (bottom == nl - 1) dev::check_rc(prfdd_dense_solve(last.u.as<double>(), Ainv.as<double>(), last.f.as<double>(), last.n, st), "dense_solve");
+        else dev::check_rc(prfdd_dense_solve(last.u.as<double>(), Bdense.as<double>(), last.f.as<double>(), last.n, st), "collapsed coarse levels");
+        for (int l = bottom; l > l0; l--)
+        {
+            Level &L = levels[l - 1];
+            Level &Lc = levels[l];
+            dev::check_rc(prfdd_csr_matvec(L.u.as<double>(), L.dP.ptr.as<int>(), L.dP.col.as<int>(), L.dP.val.as<double>(), Lc.u.as<double>(), 1.0, 1.0, L.n, L.dP.tpr, st), "prolong");
+            smooth(L, false);
+        }
+    }
+
+    // levels[0].f holds the right-hand side; result in levels[0].u
+    void vcycle(int num_vcycles)
+    {
+        for (int iter = 0; iter < num_vcycles; iter++) cycle_from(0, iter == 0);
     }
 };
 } // namespace amg

@@ -165,17 +165,19 @@ __global__ void __launch_bounds__(256) k_scatter_assign(double *__restrict__ dst
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) dst[idx[i]] = buf[i];
 }
 
+// dense x = M b, one warp per row, lanes stride through the row (coalesced), fixed-order shuffle sum.  Serves the coarsest-level
+// inverse (a handful of rows) and the collapsed coarse levels of the V-cycle (a couple of thousand rows, amg.hpp).
 __global__ void __launch_bounds__(256) k_dense_solve(double *__restrict__ x, const double *__restrict__ Ainv, const double *__restrict__ b, int n)
 {
-    extern __shared__ double sb[];
-    for (int t = threadIdx.x; t < n; t += blockDim.x) sb[t] = b[t];
-    __syncthreads();
-    for (int r = threadIdx.x; r < n; r += blockDim.x)
-    {
-        double acc = 0.0;
-        for (int c = 0; c < n; c++) acc += Ainv[(size_t)r * n + c] * sb[c];
-        x[r] = acc;
-    }
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n) return; // whole warps leave together
+    const double *__restrict__ row = Ainv + (size_t)r * n;
+    double acc = 0.0;
+    for (int c = lane; c < n; c += 32) acc += row[c] * b[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) x[r] = acc;
 }
 } // namespace prfdd
 
@@ -280,7 +282,7 @@ int prfdd_cheby_step(double *u, double *t_out, const int *ptr, const int *col, c
 int prfdd_dense_solve(double *x, const double *Ainv, const double *b, int n, prfdd_stream_t stream)
 {
     if (n <= 0) return 0;
-    k_dense_solve<<<1, 256, sizeof(double) * n, S(stream)>>>(x, Ainv, b, n);
+    k_dense_solve<<<(n + 7) / 8, 256, 0, S(stream)>>>(x, Ainv, b, n);
     return launched();
 }
 
