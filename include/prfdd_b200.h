@@ -104,7 +104,9 @@ int prfdd_scatter_assign(double *dst, const double *buf, const int *idx, int cou
  * ------------------------------------------------------------------------------------------- */
 /* every SpMV takes one launch-shape hint after the reference's argument list: threads_per_row in
  * {1,2,4,8,16,32} (a sub-warp of that many lanes walks one row with coalesced col/val reads and a
- * shuffle reduction); 0 = library default.  Callers pick it from nnz/rows of the matrix. */
+ * shuffle reduction); 0 = library default.  Callers pick it from nnz/rows of the matrix.
+ * Row-indexed arguments may be offset to run a range of rows with its own hint (ptr + r0, outputs + r0; col, val and the
+ * gathered vector unshifted). */
 /* y = A x                                        CSR_Matrix::multiply       csr_matrix.okl:5-18 */
 int prfdd_csr_multiply(double *Au, const int *ptr, const int *col, const double *val, const double *u,
                        int num_rows, int threads_per_row, prfdd_stream_t stream);

@@ -478,6 +478,9 @@ inline std::vector<double> dense_inverse(const HostCSR &A)
     return I;
 }
 
+// lanes per row from the average row length (measured on B200, profiles/r1_spmv_tpr.txt and r1_notes.txt)
+inline int lanes_per_row(double avg, int num_rows) { return avg <= 10 ? 1 : avg <= 18 ? 2 : (avg > 60 && num_rows < 50000) ? 16 : 8; }
+
 struct DeviceCSR
 {
     int num_rows = 0, num_cols = 0, nnz = 0, tpr = 4;
@@ -491,8 +494,7 @@ struct DeviceCSR
         ptr.copyFrom(A.ptr.data(), (num_rows + 1) * sizeof(int));
         col.copyFrom(A.col.data(), nnz * sizeof(int));
         val.copyFrom(A.val.data(), nnz * sizeof(double));
-        const double avg = (double)nnz / std::max(num_rows, 1);
-        tpr = avg <= 10 ? 1 : avg <= 18 ? 2 : (avg > 60 && num_rows < 50000) ? 16 : 8; // measured on B200, profiles/r1_spmv_tpr.txt and r1_notes.txt
+        tpr = lanes_per_row((double)nnz / std::max(num_rows, 1), num_rows);
     }
 };
 
@@ -568,7 +570,7 @@ class Hierarchy
         Ainv = device.malloc<double>(std::max<size_t>(Ainv_hst.size(), 1));
         Ainv.copyFrom(Ainv_hst.data(), Ainv_hst.size() * sizeof(double));
         static const bool no_collapse = getenv("PRFDD_AMG_NO_COLLAPSE") != nullptr;
-        if (!no_collapse) collapse(2048);
+        if (!no_collapse) collapse(4096);
     }
 
     void collapse(int max_rows)

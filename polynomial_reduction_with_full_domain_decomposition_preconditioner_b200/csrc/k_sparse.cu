@@ -14,17 +14,6 @@ namespace prfdd
 {
 constexpr int kSpThreads = 256;
 
-template <int TPR>
-__device__ __forceinline__ double row_dot(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, int row, int lane, bool valid)
-{
-    const int s = valid ? ptr[row] : 0, e = valid ? ptr[row + 1] : 0;
-    double acc = 0.0;
-    for (int j = s + lane; j < e; j += TPR) acc += val[j] * x[col[j]];
-#pragma unroll
-    for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, TPR);
-    return acc;
-}
-
 // generic SpMV with an epilogue functor: epi(row, Ax) executed by lane 0 of the row's sub-warp.
 // The row loop is warp-uniform (all 32 lanes take the same number of trips) so the full-mask
 // shuffles are always executed by the whole warp.  RPG > 1: every sub-warp walks RPG rows at once
@@ -39,27 +28,24 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
     const long long rows_per_grid = (long long)gridDim.x * (kSpThreads / TPR) * RPG;
     for (long long r0 = ((long long)blockIdx.x * (kSpThreads / 32) + (threadIdx.x >> 5)) * RPW * RPG; r0 < num_rows; r0 += rows_per_grid)
     {
+        int j[RPG], e[RPG];
+        double acc[RPG];
+#pragma unroll
+        for (int g = 0; g < RPG; g++)
+        {
+            const long long r = r0 + g * RPW + sub;
+            const bool valid = x && r < num_rows;
+            const int s = valid ? ptr[row_start + r] : 0;
+            e[g] = valid ? ptr[row_start + r + 1] : 0;
+            j[g] = s + lane;
+            acc[g] = 0.0;
+        }
         if constexpr (RPG == 1)
         {
-            const long long r = r0 + sub;
-            const bool valid = r < num_rows;
-            const int row = row_start + (int)r;
-            double ax = x ? row_dot<TPR>(ptr, col, val, x, row, lane, valid) : 0.0;
-            if (valid && lane == 0) epi(row, ax);
+            for (int k = j[0]; k < e[0]; k += TPR) acc[0] += val[k] * x[col[k]];
         }
         else
         {
-            int j[RPG], e[RPG];
-            double acc[RPG];
-#pragma unroll
-            for (int g = 0; g < RPG; g++)
-            {
-                const long long r = r0 + g * RPW + sub;
-                const bool valid = x && r < num_rows;
-                j[g] = valid ? ptr[row_start + r] + lane : 0;
-                e[g] = valid ? ptr[row_start + r + 1] : 0;
-                acc[g] = 0.0;
-            }
             bool more = true;
             while (more)
             {
@@ -81,14 +67,14 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
                     more |= j[g] < e[g];
                 }
             }
+        }
 #pragma unroll
-            for (int g = 0; g < RPG; g++)
-            {
+        for (int g = 0; g < RPG; g++)
+        {
 #pragma unroll
-                for (int o = TPR / 2; o > 0; o >>= 1) acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], o, TPR);
-                const long long r = r0 + g * RPW + sub;
-                if (r < num_rows && lane == 0) epi(row_start + (int)r, acc[g]);
-            }
+            for (int o = TPR / 2; o > 0; o >>= 1) acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], o, TPR);
+            const long long r = r0 + g * RPW + sub;
+            if (r < num_rows && lane == 0) epi(row_start + (int)r, acc[g]);
         }
     }
 }

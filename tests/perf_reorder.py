@@ -18,7 +18,7 @@ from perf_micro import timeit_batch as timeit, P, L, sh, PEAK  # noqa: E402
 
 def tpr_of(A):
     avg = A.nnz / A.shape[0]
-    return 1 if avg <= 10 else 2 if avg <= 18 else 4 if avg <= 44 else 8 if avg <= 60 else 16
+    return 1 if avg <= 10 else 2 if avg <= 18 else 16 if (avg > 60 and A.shape[0] < 50000) else 8
 
 
 def morton(ix, iy, iz):
@@ -38,13 +38,15 @@ def time_level(A, name):
     out = []
     flat = [-int(v) for v in os.environ.get("PRFDD_FLAT_R", "").split(",") if v]
     xh = x.cpu().numpy(); ref = A @ xh
-    for tpr in sorted({1, tpr_of(A), max(1, tpr_of(A) // 2), min(32, tpr_of(A) * 2)}) + flat:
+    caps = [int(v) for v in os.environ.get("PRFDD_CAPS", "").split(",") if v]
+    t0 = tpr_of(A)
+    for tpr in sorted({1, t0, max(1, t0 // 2), min(32, t0 * 2)}) + flat + [t0 | (c << 8) for c in caps]:
         L.prfdd_csr_multiply(P(y), P(ptr), P(col), P(val), P(x), C.c_int(nr), C.c_int(tpr), sh)
         torch.cuda.synchronize()
         err = np.abs(y.cpu().numpy() - ref).max() / np.abs(ref).max()
         assert err < 1e-13, (tpr, err)
         med, mn = timeit(lambda: L.prfdd_cheby_step(P(uu), P(y), P(ptr), P(col), P(val), P(x), P(r), P(ds), C.c_double(0.5), C.c_int(1), C.c_int(0), C.c_int(nr), C.c_int(tpr), sh))
-        out.append("tpr%d %.1fus (%.2f)" % (tpr, med * 1e3, gb / (med * 1e-3) / PEAK))
+        out.append("tpr%d%s %.1fus (%.2f)" % (tpr & 255, "/cap%d" % (tpr >> 8) if tpr >> 8 else "", med * 1e3, gb / (med * 1e-3) / PEAK))
     print("  %-14s rows %8d nnz/row %5.1f: %s" % (name, nr, A.nnz / nr, "  ".join(out)), flush=True)
 
 

@@ -256,6 +256,45 @@ def test_csr_family(G, tpr):
     G.sync(); assert np.abs(G.host(out) - ref).max() <= tol + 1e-15
 
 
+@pytest.mark.parametrize("tpr", [1, 2, 8, 32])
+@pytest.mark.parametrize("nr", [4097, 300001])   # the large case takes the two-rows-per-sub-warp variant for tpr >= 8
+def test_csr_ragged_rows_and_row_ranges(G, tpr, nr):
+    """rows of very different lengths: empty rows, short rows, a few rows of several hundred entries (the hanging-node rows of the
+    composite grid), whole matrix with one lanes-per-row hint and as two pointer-offset row ranges with different hints (what the
+    AMG levels do for the ranges that hold long rows) -- all against the oracle's scalar loop"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(100 * tpr)
+    lib, L = G.lib, oc.lib()
+    nc = nr
+    lens = rng.integers(0, 9, nr)
+    lens[rng.integers(0, nr, 40)] = rng.integers(60, 700, 40)
+    lens[:3] = [0, 650, 1]; lens[-2:] = [333, 0]
+    ptr = np.zeros(nr + 1, np.int32); ptr[1:] = np.cumsum(lens)
+    steps = rng.integers(1, 4, ptr[-1])                       # strictly increasing columns inside every row
+    run = np.cumsum(steps)
+    row_of = np.repeat(np.arange(nr), lens)
+    first = np.concatenate([[0], run[:-1]])[ptr[:-1].clip(max=max(ptr[-1] - 1, 0))]
+    col = (rng.integers(0, nc - 3 * 700 - 4, nr)[row_of] + run - first[row_of]).astype(np.int32)
+    val = rng.standard_normal(ptr[-1])
+    u = rng.standard_normal(nc); f = rng.standard_normal(nr)
+    A = sp.csr_matrix((val, col, ptr), shape=(nr, nc))
+    tol = 8e-15 * (np.abs(A) @ np.abs(u)).max()
+    dptr, dcol, dval, du, df = (G.dev(x) for x in (ptr, col, val, u, f))
+    ref = np.zeros(nr); L.o_csr_multiply(P(ref), P(ptr), P(col), P(val), P(u), C.c_int(nr))
+    out = G.dev(np.full(nr, 7.0))
+    assert lib.prfdd_csr_multiply(G.p(out), G.p(dptr), G.p(dcol), G.p(dval), G.p(du), C.c_int(nr), C.c_int(tpr), G.stream()) == 0
+    G.sync(); got = G.host(out)
+    assert np.abs(got - ref).max() <= tol and got[0] == 0.0 and got[-1] == 0.0
+    # two row ranges, pointer-offset: rows [0, r0) with `tpr`, rows [r0, nr) with 8 lanes per row
+    r0 = 1024 * (nr // 2048)
+    out2 = G.dev(np.full(nr, 7.0))
+    off = lambda t, k, item: C.c_void_p(t.data_ptr() + k * item)
+    assert lib.prfdd_csr_residual(G.p(out2), G.p(dptr), G.p(dcol), G.p(dval), G.p(du), G.p(df), C.c_int(r0), C.c_int(tpr), G.stream()) == 0
+    assert lib.prfdd_csr_residual(off(out2, r0, 8), off(dptr, r0, 4), G.p(dcol), G.p(dval), G.p(du), off(df, r0, 8), C.c_int(nr - r0), C.c_int(8), G.stream()) == 0
+    G.sync(); assert np.abs(G.host(out2) - (f - ref)).max() <= tol
+    assert lib.prfdd_csr_multiply(G.p(out), G.p(dptr), G.p(dcol), G.p(dval), G.p(du), C.c_int(nr), C.c_int(3), G.stream()) == -6
+
+
 def test_chebyshev_smoother_matches_reference_sequence(G):
     """One Chebyshev smoothing (order 2 and 3) through the fused kernels vs the reference's sequence
     scaled_residual -> polynomial_evaluation -> update_field (subdomain.tpp:19-83, host branches)."""
