@@ -107,6 +107,12 @@ int prfdd_scatter_assign(double *dst, const double *buf, const int *idx, int cou
  * shuffle reduction); 0 = library default.  Callers pick it from nnz/rows of the matrix.
  * Row-indexed arguments may be offset to run a range of rows with its own hint (ptr + r0, outputs + r0; col, val and the
  * gathered vector unshifted). */
+/* Long rows: a thread (or sub-warp) that walks a row many times the average length alone outlasts the rest of the kernel.
+ * A matrix may register the device list of its rows longer than `threshold` entries, keyed by the device address of its
+ * row-pointer array; every SpMV of this family called with that `ptr` (whole matrix, not a row range) then leaves those
+ * rows to a second launch that gives each a whole warp.  count = 0 clears the registration; call it whenever a row-pointer
+ * array is (re)uploaded so that a recycled address cannot keep a stale list.  Host-side state of the calling process. */
+int prfdd_csr_set_long_rows(const int *ptr, const int *long_rows, int count, int threshold);
 /* y = A x                                        CSR_Matrix::multiply       csr_matrix.okl:5-18 */
 int prfdd_csr_multiply(double *Au, const int *ptr, const int *col, const double *val, const double *u,
                        int num_rows, int threads_per_row, prfdd_stream_t stream);

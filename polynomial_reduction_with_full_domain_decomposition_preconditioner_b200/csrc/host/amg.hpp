@@ -26,6 +26,7 @@
 #include <numeric>
 #include <vector>
 #include "config.hpp"
+#include "csr_matrix.hpp"
 #include "../../../include/prfdd_b200.h"
 
 namespace amg
@@ -484,7 +485,7 @@ inline int lanes_per_row(double avg, int num_rows) { return avg <= 10 ? 1 : avg 
 struct DeviceCSR
 {
     int num_rows = 0, num_cols = 0, nnz = 0, tpr = 4;
-    dev::memory ptr, col, val;
+    dev::memory ptr, col, val, long_rows;
     void upload(const HostCSR &A)
     {
         num_rows = A.num_rows; num_cols = A.num_cols; nnz = A.nnz();
@@ -494,7 +495,9 @@ struct DeviceCSR
         ptr.copyFrom(A.ptr.data(), (num_rows + 1) * sizeof(int));
         col.copyFrom(A.col.data(), nnz * sizeof(int));
         val.copyFrom(A.val.data(), nnz * sizeof(double));
-        tpr = lanes_per_row((double)nnz / std::max(num_rows, 1), num_rows);
+        const double avg = (double)nnz / std::max(num_rows, 1);
+        tpr = lanes_per_row(avg, num_rows);
+        long_rows = ::register_long_rows(ptr.as<int>(), A.ptr.data(), num_rows, avg, tpr);
     }
 };
 

@@ -13,11 +13,39 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <tuple>
 #include <typeinfo>
 #include <vector>
 #include "config.hpp"
 #include "../../../include/prfdd_b200.h"
+
+// rows much longer than the average (and than the lanes that walk them can absorb) go to the warp-per-row launch
+// (prfdd_csr_set_long_rows); returns the device list that must stay alive with the matrix
+inline dev::memory register_long_rows(const int *ptr_dev, const int *ptr_hst, int num_rows, double avg, int tpr)
+{
+    static const bool off = getenv("PRFDD_SPMV_NO_LONG_ROWS") != nullptr;
+    const int threshold = std::max(std::max(16, 4 * tpr), (int)std::ceil(3.0 * avg));
+    std::vector<int> rows;
+    int longest = 0;
+    for (int r = 0; r < num_rows && !off; r++)
+    {
+        const int len = ptr_hst[r + 1] - ptr_hst[r];
+        longest = std::max(longest, len);
+        if (len > threshold) rows.push_back(r);
+    }
+    dev::memory list;
+    // worth a second launch only when some row is several times the threshold (the tail it removes is then longer than the launch)
+    if (rows.empty() || tpr >= 32 || longest < 4 * threshold || (double)rows.size() > 0.05 * num_rows)
+    {
+        prfdd_csr_set_long_rows(ptr_dev, nullptr, 0, 0);
+        return list;
+    }
+    list = prfdd_host::device.malloc<int>(rows.size());
+    list.copyFrom(rows.data(), rows.size() * sizeof(int));
+    prfdd_csr_set_long_rows(ptr_dev, list.as<int>(), (int)rows.size(), threshold);
+    return list;
+}
 
 template <typename DType>
 class CSR_Matrix
@@ -49,6 +77,7 @@ class CSR_Matrix
     std::vector<int> col_hst;
     std::vector<DType> val_hst;
     int threads_per_row = 1;
+    dev::memory long_rows; // rows given a whole warp (prfdd_csr_set_long_rows)
 
     CSR_Matrix() {}
     CSR_Matrix(int num_rows_, int num_cols_) { initialize(num_rows_, num_cols_); }
@@ -132,6 +161,7 @@ class CSR_Matrix
         val.copyFrom(val_hst.data(), num_nnz * sizeof(DType));
         double avg = (double)num_nnz / (double)std::max(num_rows, 1);
         threads_per_row = avg <= 10 ? 1 : avg <= 18 ? 2 : (avg > 60 && num_rows < 50000) ? 16 : 8; // measured on B200, profiles/r1_spmv_tpr.txt and r1_notes.txt
+        long_rows = register_long_rows(ptr.as<int>(), ptr_hst.data(), num_rows, avg, threads_per_row);
     }
 
     void print(FILE *file_ptr = NULL, int offset = 0)

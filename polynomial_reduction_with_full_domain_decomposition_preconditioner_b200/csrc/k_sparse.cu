@@ -9,6 +9,7 @@
 // around an SpMV (scaling by ds, c*r + v, u += ds*w, f - A u) is done in the SpMV epilogue, so one
 // Chebyshev smoothing of order 2 is 2 launches and 2 passes over A instead of 7 launches.
 #include "common.cuh"
+#include <unordered_map>
 
 namespace prfdd
 {
@@ -20,7 +21,7 @@ constexpr int kSpThreads = 256;
 // (rows r, r + 32/TPR, ...), which multiplies the independent col/val -> x load chains a lane has in
 // flight; the long rows of the coarse AMG levels are latency bound without it.
 template <int TPR, int RPG, class Epi>
-__global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, int row_start, int num_rows, Epi epi)
+__global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, int row_start, int num_rows, int skip_len, Epi epi)
 {
     constexpr int RPW = 32 / TPR; // rows per warp and pass
     const int lane = threadIdx.x % TPR;
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
     for (long long r0 = ((long long)blockIdx.x * (kSpThreads / 32) + (threadIdx.x >> 5)) * RPW * RPG; r0 < num_rows; r0 += rows_per_grid)
     {
         int j[RPG], e[RPG];
+        bool skip[RPG];
         double acc[RPG];
 #pragma unroll
         for (int g = 0; g < RPG; g++)
@@ -37,6 +39,8 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
             const bool valid = x && r < num_rows;
             const int s = valid ? ptr[row_start + r] : 0;
             e[g] = valid ? ptr[row_start + r + 1] : 0;
+            skip[g] = e[g] - s > skip_len; // a listed long row: k_spmv_long owns it
+            if (skip[g]) e[g] = s;
             j[g] = s + lane;
             acc[g] = 0.0;
         }
@@ -74,20 +78,48 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
 #pragma unroll
             for (int o = TPR / 2; o > 0; o >>= 1) acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], o, TPR);
             const long long r = r0 + g * RPW + sub;
-            if (r < num_rows && lane == 0) epi(row_start + (int)r, acc[g]);
+            if (r < num_rows && lane == 0 && !skip[g]) epi(row_start + (int)r, acc[g]);
         }
     }
 }
 
+// Long rows.  A warp finishes when its longest row does, and under load one dependent col -> x step costs microseconds, so a
+// thread that walks a 60- or 300-entry row alone (hanging-node rows of the non-conforming composite grid in the low-order
+// matrix, and the columns of its Q that become rows of Q^T) outlasts the rest of the kernel.  Matrices can register the
+// list of their rows longer than a threshold (prfdd_csr_set_long_rows): k_spmv then skips those rows and k_spmv_long gives
+// each a whole warp.  Same epilogue, fixed summation order.
+template <class Epi>
+__global__ void __launch_bounds__(kSpThreads) k_spmv_long(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, const int *__restrict__ rows, int count, Epi epi)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (kSpThreads / 32) + (threadIdx.x >> 5);
+    if (w >= count) return; // whole warps leave together
+    const int row = rows[w];
+    double acc = 0.0;
+    for (int j = ptr[row] + lane; j < ptr[row + 1]; j += 32) acc += val[j] * x[col[j]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) epi(row, acc);
+}
+
+struct LongRows
+{
+    const int *rows;
+    int count, threshold;
+};
+static std::unordered_map<const void *, LongRows> g_long_rows; // keyed by the device address of the row-pointer array
+
 template <int TPR, class Epi>
-static void launch_spmv(const int *ptr, const int *col, const double *val, const double *x, int row_start, int num_rows, cudaStream_t st, Epi epi)
+static void launch_spmv(const int *ptr, const int *col, const double *val, const double *x, int row_start, int num_rows, const LongRows *lr, cudaStream_t st, Epi epi)
 {
     // two rows per sub-warp once the matrix is large enough to fill the machine with half as many warps
     // (AMG level 1 of the 16^3 N=7 problem, 27 entries/row: 54.9 -> 49.1 us; profiles/r1_notes.txt)
     const bool two = TPR >= 4 && (long long)num_rows * TPR >= (1ll << 21);
     const int grid = stream_grid((long long)num_rows * TPR / (two ? 2 : 1), kSpThreads, 1, 16);
-    if (two) k_spmv<TPR, 2><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, epi);
-    else k_spmv<TPR, 1><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, epi);
+    const int skip_len = lr ? lr->threshold : 0x7fffffff;
+    if (two) k_spmv<TPR, 2><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, skip_len, epi);
+    else k_spmv<TPR, 1><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, skip_len, epi);
+    if (lr) k_spmv_long<<<(lr->count + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(ptr, col, val, x, lr->rows, lr->count, epi);
 }
 
 template <class Epi>
@@ -95,16 +127,23 @@ static int spmv(const int *ptr, const int *col, const double *val, const double 
 {
     if (num_rows <= 0) return 0;
     if (tpr <= 0) tpr = 4;
+    const LongRows *lr = nullptr;
+    if (x && row_start == 0 && tpr < 32 && !g_long_rows.empty())
+    {
+        auto it = g_long_rows.find(ptr);
+        if (it != g_long_rows.end()) lr = &it->second;
+    }
     switch (tpr)
     {
-    case 1: launch_spmv<1>(ptr, col, val, x, row_start, num_rows, st, epi); break;
-    case 2: launch_spmv<2>(ptr, col, val, x, row_start, num_rows, st, epi); break;
-    case 4: launch_spmv<4>(ptr, col, val, x, row_start, num_rows, st, epi); break;
-    case 8: launch_spmv<8>(ptr, col, val, x, row_start, num_rows, st, epi); break;
-    case 16: launch_spmv<16>(ptr, col, val, x, row_start, num_rows, st, epi); break;
-    case 32: launch_spmv<32>(ptr, col, val, x, row_start, num_rows, st, epi); break;
+    case 1: launch_spmv<1>(ptr, col, val, x, row_start, num_rows, lr, st, epi); break;
+    case 2: launch_spmv<2>(ptr, col, val, x, row_start, num_rows, lr, st, epi); break;
+    case 4: launch_spmv<4>(ptr, col, val, x, row_start, num_rows, lr, st, epi); break;
+    case 8: launch_spmv<8>(ptr, col, val, x, row_start, num_rows, lr, st, epi); break;
+    case 16: launch_spmv<16>(ptr, col, val, x, row_start, num_rows, lr, st, epi); break;
+    case 32: launch_spmv<32>(ptr, col, val, x, row_start, num_rows, lr, st, epi); break;
     default: return -6;
     }
+    if (lr) prfdd_launch_count_add(1);
     return launched();
 }
 
@@ -204,6 +243,14 @@ int prfdd_scatter_assign(double *dst, const double *buf, const int *idx, int cou
     if (count <= 0) return 0;
     k_scatter_assign<<<stream_grid(count, 256, 1, 8), 256, 0, S(stream)>>>(dst, buf, idx, count);
     return launched();
+}
+
+int prfdd_csr_set_long_rows(const int *ptr, const int *rows, int count, int threshold)
+{
+    if (!ptr) return -8;
+    if (!rows || count <= 0) g_long_rows.erase(ptr);
+    else g_long_rows[ptr] = LongRows{rows, count, threshold};
+    return 0;
 }
 
 int prfdd_csr_multiply(double *Au, const int *ptr, const int *col, const double *val, const double *u, int num_rows, int tpr, prfdd_stream_t stream)

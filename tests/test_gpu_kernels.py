@@ -293,6 +293,15 @@ def test_csr_ragged_rows_and_row_ranges(G, tpr, nr):
     assert lib.prfdd_csr_residual(off(out2, r0, 8), off(dptr, r0, 4), G.p(dcol), G.p(dval), G.p(du), off(df, r0, 8), C.c_int(nr - r0), C.c_int(8), G.stream()) == 0
     G.sync(); assert np.abs(G.host(out2) - (f - ref)).max() <= tol
     assert lib.prfdd_csr_multiply(G.p(out), G.p(dptr), G.p(dcol), G.p(dval), G.p(du), C.c_int(nr), C.c_int(3), G.stream()) == -6
+    # registered long rows: the listed rows are left to the warp-per-row launch, everything else as before
+    T = 24
+    long_rows = np.flatnonzero(lens > T).astype(np.int32)
+    dlr = G.dev(long_rows)
+    assert lib.prfdd_csr_set_long_rows(G.p(dptr), G.p(dlr), C.c_int(len(long_rows)), C.c_int(T)) == 0
+    out3 = G.dev(np.full(nr, 7.0))
+    assert lib.prfdd_csr_residual(G.p(out3), G.p(dptr), G.p(dcol), G.p(dval), G.p(du), G.p(df), C.c_int(nr), C.c_int(tpr), G.stream()) == 0
+    G.sync(); assert np.abs(G.host(out3) - (f - ref)).max() <= tol
+    assert lib.prfdd_csr_set_long_rows(G.p(dptr), None, C.c_int(0), C.c_int(0)) == 0
 
 
 def test_chebyshev_smoother_matches_reference_sequence(G):
