@@ -147,6 +147,28 @@ def cpu_baseline(nel):
             "sample": "oracle port (C kernels = OCCA-Serial loops) on the box's host CPU: 3D %d^3 hex box, N=7 (%d nodes), %d full PR-FDD PCG solves to 1e-8, setup excluded" % (nel, nodes, reps)}
 
 
+def ncu_traffic(o):
+    """DRAM bytes per launch (read + write) of the roofline kernel from the committed `ncu --set full` capture
+    (profiles/r1_ncu_traffic.json), averaged over the two levels bench alternates -- only if the capture is of these very matrices
+    (same rows / nnz), else null"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))["cheby_step"]
+        l0, l1 = t["level0"], t["level1"]
+        if (l0["rows"], l0["nnz"], l1["rows"], l1["nnz"]) == (int(o[2]), int(o[3]), int(o[4]), int(o[5])):
+            return 0.5 * (l0["dram_bytes"] + l1["dram_bytes"])
+    except Exception:
+        pass
+    return None
+
+
+def operator_traffic(E, n):
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))["k_ax3d_bulk"]
+        return float(t["dram_bytes"]) if (t["elements"], t["n"]) == (E, n) else None
+    except Exception:
+        return None
+
+
 def kernel_roofline(pr, torch, stream, peaks, peaks_kind):
     """average launch duration of the dominant kernel, measured with CUDA events on the launching stream,
     on device data of the workload's size: the fused Chebyshev SpMV step on the level-0 low-order FEM matrix
@@ -186,7 +208,7 @@ def kernel_roofline(pr, torch, stream, peaks, peaks_kind):
     bytes_alg = 64.0 * P                                  # u 8 + six G 48 + Au 8 per point
     achieved = bytes_alg / (t_ms * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": "k_ax3d_bulk<8> (prfdd_stiffness_matrix, 4096 elements, n=8)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peaks_kind == "measured" else "fallback 6.65 TB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": operator_traffic(E, n), "peak_source": peaks_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peaks_kind == "measured" else "fallback 6.65 TB/s",
             "avg_launch_ms": t_ms, "algorithmic_bytes_per_launch": bytes_alg}
 
 
@@ -295,8 +317,12 @@ def main():
         step_host()
     sampler = ClockSampler(local)
     sampler.start()
+    # cudaProfilerStart/Stop around the timed steps: `ncu --profile-from-start off ... python bench.py ...` then lists exactly the
+    # launches of the timed region (set-up alone makes ~60k launches); a no-op without a profiler
+    torch.cuda.cudart().cudaProfilerStart()
     ms, iters, launches = timed(step_dev, args.steps)
     ms_e2e, iters_e2e, _ = timed(step_host, args.steps)
+    torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.stop()
     value = nodes * iters / (ms * 1e-3) / 1e9
     e2e = nodes * iters_e2e / (ms_e2e * 1e-3) / 1e9
@@ -316,7 +342,7 @@ def main():
                 ach = o[1] / (o[0] * 1e-3) / 1e9
                 roof = {"bound": "hbm", "kernel": "k_spmv<TPR> + Chebyshev epilogue (prfdd_cheby_step) on AMG levels 0 and 1 of the low-order FEM hierarchy, alternating "
                         "(level 0: %d rows, %d nnz; level 1: %d rows, %d nnz) -- the SpMV family is the dominant kernel of the solve (profiles/)" % (o[2], o[3], o[4], o[5]),
-                        "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                        "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic(o),
                         "peak_source": roof_op["peak_source"], "avg_launch_ms": o[0], "algorithmic_bytes_per_launch": o[1]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

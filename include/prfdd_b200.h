@@ -143,6 +143,10 @@ int prfdd_vector_multiplication(double *uv, const double *u, const double *v, in
 int prfdd_cheby_residual(double *r, double *t, const int *ptr, const int *col, const double *val, const double *u,
                          const double *f, const double *ds, double c_hi, int num_rows, int threads_per_row,
                          prfdd_stream_t stream);
+/* restriction fused with the head of the next level's zero-guess smoothing: f = R v, r = ds f, t = ds (c_hi r)
+ * (= prfdd_csr_multiply followed by prfdd_cheby_residual with u = NULL on the coarse level; one pass, one launch) */
+int prfdd_restrict_cheby_residual(double *f, double *r, double *t, const int *ptr, const int *col, const double *val, const double *v,
+                                  const double *ds, double c_hi, int num_rows, int threads_per_row, prfdd_stream_t stream);
 /* fused Chebyshev Horner step: w = c*r + ds.*(A t_in); if last: u (+)= ds.*w else t_out = ds.*w
  * replaces polynomial_evaluation (+ update_field), subdomain.tpp:45-83.  u_is_zero: u = ds.*w */
 int prfdd_cheby_step(double *u, double *t_out, const int *ptr, const int *col, const double *val, const double *t_in,

@@ -607,14 +607,15 @@ class Hierarchy
     }
 
     // hypre-style Chebyshev smoothing: r = ds(f - A u); w = c[k-1] r; for p = k-2..0: w = c[p] r + ds A ds w; u += ds w
-    void smooth(Level &L, bool u_is_zero)
+    void smooth(Level &L, bool u_is_zero, bool residual_done = false)
     {
         cudaStream_t st = prfdd_host::device.stream;
         const int k = cheby_order;
         double *u = L.u.as<double>(), *r = L.r.as<double>(), *t0 = L.t0.as<double>(), *t1 = L.t1.as<double>();
         const int *ptr = L.dA.ptr.as<int>(), *col = L.dA.col.as<int>();
         const double *val = L.dA.val.as<double>(), *ds = L.ds.as<double>(), *f = L.f.as<double>();
-        dev::check_rc(prfdd_cheby_residual(r, t0, ptr, col, val, u_is_zero ? nullptr : u, f, ds, L.coefs[k - 1], L.n, L.dA.tpr, st), "cheby_residual");
+        // residual_done: the restriction that produced f already wrote r and t0 (prfdd_restrict_cheby_residual)
+        if (!residual_done) dev::check_rc(prfdd_cheby_residual(r, t0, ptr, col, val, u_is_zero ? nullptr : u, f, ds, L.coefs[k - 1], L.n, L.dA.tpr, st), "cheby_residual");
         if (k == 1)
         {
             dev::check_rc(prfdd_cheby_order1(u, r, ds, L.coefs[0], u_is_zero ? 1 : 0, L.n, st), "cheby_order1");
@@ -637,10 +638,14 @@ class Hierarchy
         for (int l = l0; l < bottom; l++)
         {
             Level &L = levels[l];
-            smooth(L, l > l0 || first_guess_is_zero);
+            smooth(L, l > l0 || first_guess_is_zero, l > l0);
             dev::check_rc(prfdd_csr_residual(L.v.as<double>(), L.dA.ptr.as<int>(), L.dA.col.as<int>(), L.dA.val.as<double>(), L.u.as<double>(), L.f.as<double>(), L.n, L.dA.tpr, st), "csr_residual");
             Level &Lc = levels[l + 1];
-            dev::check_rc(prfdd_csr_multiply(Lc.f.as<double>(), L.dR.ptr.as<int>(), L.dR.col.as<int>(), L.dR.val.as<double>(), L.v.as<double>(), Lc.n, L.dR.tpr, st), "restrict");
+            if (l + 1 < bottom) // the coarse level is smoothed next: fuse the head of that smoothing into the restriction
+                dev::check_rc(prfdd_restrict_cheby_residual(Lc.f.as<double>(), Lc.r.as<double>(), Lc.t0.as<double>(), L.dR.ptr.as<int>(), L.dR.col.as<int>(), L.dR.val.as<double>(), L.v.as<double>(),
+                                                            Lc.ds.as<double>(), Lc.coefs[cheby_order - 1], Lc.n, L.dR.tpr, st), "restrict + residual");
+            else
+                dev::check_rc(prfdd_csr_multiply(Lc.f.as<double>(), L.dR.ptr.as<int>(), L.dR.col.as<int>(), L.dR.val.as<double>(), L.v.as<double>(), Lc.n, L.dR.tpr, st), "restrict");
         }
         Level &last = levels[bottom];
         if (bottom == nl - 1) dev::check_rc(prfdd_dense_solve(last.u.as<double>(), Ainv.as<double>(), last.f.as<double>(), last.n, st), "dense_solve");

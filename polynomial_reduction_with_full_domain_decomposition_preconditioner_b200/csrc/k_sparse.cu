@@ -292,6 +292,18 @@ int prfdd_cheby_residual(double *r, double *t, const int *ptr, const int *col, c
     });
 }
 
+int prfdd_restrict_cheby_residual(double *f, double *r, double *t, const int *ptr, const int *col, const double *val, const double *v, const double *ds, double c_hi, int num_rows, int tpr, prfdd_stream_t stream)
+{
+    // f = R v fused with the zero-guess head of the coarse level's smoothing: r = ds f, t = ds (c_hi r)
+    return spmv(ptr, col, val, v, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) {
+        const double d = ds[row];
+        const double rr = d * ax;
+        f[row] = ax;
+        r[row] = rr;
+        t[row] = d * (c_hi * rr);
+    });
+}
+
 int prfdd_cheby_step(double *u, double *t_out, const int *ptr, const int *col, const double *val, const double *t_in, const double *r, const double *ds, double c, int last, int u_is_zero, int num_rows, int tpr, prfdd_stream_t stream)
 {
     if (last)

@@ -304,6 +304,26 @@ def test_csr_ragged_rows_and_row_ranges(G, tpr, nr):
     assert lib.prfdd_csr_set_long_rows(G.p(dptr), None, C.c_int(0), C.c_int(0)) == 0
 
 
+def test_restrict_fused_with_smoothing_head(G):
+    """prfdd_restrict_cheby_residual == prfdd_csr_multiply followed by prfdd_cheby_residual(u = NULL), bit for bit"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(5)
+    lib = G.lib
+    nc, nf = 1500, 4000
+    R = sp.random(nc, nf, density=0.003, random_state=5, format="csr"); R.sort_indices()
+    ptr, col, val = R.indptr.astype(np.int32), R.indices.astype(np.int32), np.ascontiguousarray(R.data)
+    v = rng.standard_normal(nf); ds = rng.uniform(0.5, 2.0, nc); c_hi = 0.37
+    dptr, dcol, dval, dv, dds = (G.dev(x) for x in (ptr, col, val, v, ds))
+    f1, r1, t1, f2, r2, t2 = (G.dev(np.full(nc, 9.0)) for _ in range(6))
+    for tpr in (1, 4):
+        assert lib.prfdd_csr_multiply(G.p(f1), G.p(dptr), G.p(dcol), G.p(dval), G.p(dv), C.c_int(nc), C.c_int(tpr), G.stream()) == 0
+        assert lib.prfdd_cheby_residual(G.p(r1), G.p(t1), G.p(dptr), G.p(dcol), G.p(dval), None, G.p(f1), G.p(dds), C.c_double(c_hi), C.c_int(nc), C.c_int(tpr), G.stream()) == 0
+        assert lib.prfdd_restrict_cheby_residual(G.p(f2), G.p(r2), G.p(t2), G.p(dptr), G.p(dcol), G.p(dval), G.p(dv), G.p(dds), C.c_double(c_hi), C.c_int(nc), C.c_int(tpr), G.stream()) == 0
+        G.sync()
+        assert np.array_equal(G.host(f1), G.host(f2)) and np.array_equal(G.host(r1), G.host(r2)) and np.array_equal(G.host(t1), G.host(t2))
+        assert np.abs(G.host(f2) - R @ v).max() < 1e-13
+
+
 def test_chebyshev_smoother_matches_reference_sequence(G):
     """One Chebyshev smoothing (order 2 and 3) through the fused kernels vs the reference's sequence
     scaled_residual -> polynomial_evaluation -> update_field (subdomain.tpp:19-83, host branches)."""
