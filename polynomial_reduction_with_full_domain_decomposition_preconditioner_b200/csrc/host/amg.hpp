@@ -19,8 +19,12 @@
 //     surrounding preconditioner application.
 #pragma once
 #include <algorithm>
+#include <atomic>
+#include <thread>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -52,6 +56,75 @@ inline uint64_t splitmix64(uint64_t x)
 inline uint64_t hash_of(uint64_t idx, uint64_t salt) { return splitmix64(idx + (salt << 32)); }
 inline double hashed_unit(uint64_t idx, uint64_t salt) { return (double)(hash_of(idx, salt) >> 11) * (1.0 / 9007199254740992.0); }
 
+// Row-parallel set-up on the host.  The rows of a sparse product or of the interpolation are independent, so they are cut into
+// contiguous chunks handed out dynamically to a few std::threads (each with its own scratch arrays); the chunks are concatenated
+// in row order, so the result is bit-identical to the serial loop whatever the thread count.  PRFDD_HOST_THREADS overrides.
+inline int host_threads(int n)
+{
+    if (n < 20000) return 1;
+    static const int configured = [] {
+        const char *e = getenv("PRFDD_HOST_THREADS");
+        if (e) return std::max(1, atoi(e));
+        const int hw = (int)std::thread::hardware_concurrency();
+        return std::max(1, std::min(16, hw / std::max(1, prfdd_host::num_procs)));
+    }();
+    return configured;
+}
+
+struct RowChunk
+{
+    int lo = 0, hi = 0;
+    std::vector<int> len, col; // len[r - lo] = entries of row r
+    std::vector<double> val;
+};
+
+// body(scratch_owner_thread, chunk) fills chunk.len / col / val for rows [chunk.lo, chunk.hi)
+template <class MakeScratch, class Body>
+inline HostCSR build_rows_parallel(int num_rows, int num_cols, MakeScratch make_scratch, Body body)
+{
+    const int T = host_threads(num_rows);
+    const int nchunks = T == 1 ? 1 : 8 * T;
+    std::vector<RowChunk> chunks(nchunks);
+    for (int c = 0; c < nchunks; c++)
+    {
+        chunks[c].lo = (int)((long long)num_rows * c / nchunks);
+        chunks[c].hi = (int)((long long)num_rows * (c + 1) / nchunks);
+    }
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+        auto scratch = make_scratch();
+        for (int c = next++; c < nchunks; c = next++)
+        {
+            chunks[c].len.reserve(chunks[c].hi - chunks[c].lo);
+            body(scratch, chunks[c]);
+        }
+    };
+    if (T == 1) worker();
+    else
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; t++) pool.emplace_back(worker);
+        for (auto &th : pool) th.join();
+    }
+    HostCSR M;
+    M.num_rows = num_rows;
+    M.num_cols = num_cols;
+    M.ptr.assign(num_rows + 1, 0);
+    size_t total = 0;
+    for (auto &ch : chunks) total += ch.col.size();
+    M.col.resize(total);
+    M.val.resize(total);
+    size_t at = 0;
+    for (auto &ch : chunks)
+    {
+        for (int r = ch.lo; r < ch.hi; r++) M.ptr[r + 1] = M.ptr[r] + ch.len[r - ch.lo];
+        std::copy(ch.col.begin(), ch.col.end(), M.col.begin() + at);
+        std::copy(ch.val.begin(), ch.val.end(), M.val.begin() + at);
+        at += ch.col.size();
+    }
+    return M;
+}
+
 inline HostCSR transpose(const HostCSR &A)
 {
     HostCSR T;
@@ -77,41 +150,43 @@ inline HostCSR transpose(const HostCSR &A)
 // then the entries of row k of B)
 inline HostCSR spgemm(const HostCSR &A, const HostCSR &B)
 {
-    HostCSR Cm;
-    Cm.num_rows = A.num_rows;
-    Cm.num_cols = B.num_cols;
-    Cm.ptr.assign(A.num_rows + 1, 0);
-    std::vector<int> marker(B.num_cols, -1);
-    std::vector<double> acc(B.num_cols, 0.0);
-    std::vector<int> cols;
-    for (int i = 0; i < A.num_rows; i++)
+    struct Scratch
     {
-        cols.clear();
-        for (int ja = A.ptr[i]; ja < A.ptr[i + 1]; ja++)
-        {
-            const int k = A.col[ja];
-            const double a = A.val[ja];
-            for (int jb = B.ptr[k]; jb < B.ptr[k + 1]; jb++)
+        std::vector<int> marker, cols;
+        std::vector<double> acc;
+    };
+    return build_rows_parallel(
+        A.num_rows, B.num_cols,
+        [&] { Scratch s; s.marker.assign(B.num_cols, -1); s.acc.assign(B.num_cols, 0.0); return s; },
+        [&](Scratch &s, RowChunk &ch) {
+            for (int i = ch.lo; i < ch.hi; i++)
             {
-                const int c = B.col[jb];
-                if (marker[c] != i)
+                s.cols.clear();
+                for (int ja = A.ptr[i]; ja < A.ptr[i + 1]; ja++)
                 {
-                    marker[c] = i;
-                    acc[c] = 0.0;
-                    cols.push_back(c);
+                    const int k = A.col[ja];
+                    const double a = A.val[ja];
+                    for (int jb = B.ptr[k]; jb < B.ptr[k + 1]; jb++)
+                    {
+                        const int c = B.col[jb];
+                        if (s.marker[c] != i)
+                        {
+                            s.marker[c] = i;
+                            s.acc[c] = 0.0;
+                            s.cols.push_back(c);
+                        }
+                        s.acc[c] += a * B.val[jb];
+                    }
                 }
-                acc[c] += a * B.val[jb];
+                std::sort(s.cols.begin(), s.cols.end());
+                for (int c : s.cols)
+                {
+                    ch.col.push_back(c);
+                    ch.val.push_back(s.acc[c]);
+                }
+                ch.len.push_back((int)s.cols.size());
             }
-        }
-        std::sort(cols.begin(), cols.end());
-        for (int c : cols)
-        {
-            Cm.col.push_back(c);
-            Cm.val.push_back(acc[c]);
-        }
-        Cm.ptr[i + 1] = (int)Cm.col.size();
-    }
-    return Cm;
+        });
 }
 
 // S[i] = { j != i : -a_ij >= theta * max_k(-a_ik) > 0 }
@@ -210,21 +285,26 @@ inline HostCSR interp_extpi(const HostCSR &A, const std::vector<int> &Sptr, cons
             if (A.col[j] == i) diag[i] = A.val[j];
     auto sgn = [](double x) { return (x > 0.0) - (x < 0.0); };
 
-    HostCSR P;
-    P.num_rows = n;
-    P.num_cols = nc;
-    P.ptr.assign(n + 1, 0);
-    std::vector<int> strong_stamp(n, -1), chat_stamp(n, -1);
-    std::vector<double> num(n, 0.0);
-    std::vector<int> chat;
-    std::vector<std::pair<int, double>> cand;
-    for (int i = 0; i < n; i++)
+    struct Scratch
     {
+        std::vector<int> strong_stamp, chat_stamp, chat;
+        std::vector<double> num;
+        std::vector<std::pair<int, double>> cand;
+    };
+    return build_rows_parallel(
+        n, nc, [&] { Scratch s; s.strong_stamp.assign(n, -1); s.chat_stamp.assign(n, -1); s.num.assign(n, 0.0); return s; },
+        [&](Scratch &sc, RowChunk &P) {
+    std::vector<int> &strong_stamp = sc.strong_stamp, &chat_stamp = sc.chat_stamp, &chat = sc.chat;
+    std::vector<double> &num = sc.num;
+    std::vector<std::pair<int, double>> &cand = sc.cand;
+    for (int i = P.lo; i < P.hi; i++)
+    {
+        const size_t row_begin = P.col.size();
         if (cf[i] == 1)
         {
             P.col.push_back(cidx[i]);
             P.val.push_back(1.0);
-            P.ptr[i + 1] = (int)P.col.size();
+            P.len.push_back(1);
             continue;
         }
         chat.clear();
@@ -329,19 +409,26 @@ inline HostCSR interp_extpi(const HostCSR &A, const std::vector<int> &Sptr, cons
                 P.val.push_back(cw.second);
             }
         }
-        P.ptr[i + 1] = (int)P.col.size();
+        P.len.push_back((int)(P.col.size() - row_begin));
     }
-    return P;
+        });
 }
 
 inline void spmv(const HostCSR &A, const double *x, double *y)
 {
-    for (int i = 0; i < A.num_rows; i++)
-    {
-        double s = 0.0;
-        for (int j = A.ptr[i]; j < A.ptr[i + 1]; j++) s += A.val[j] * x[A.col[j]];
-        y[i] = s;
-    }
+    auto rows = [&](int lo, int hi) {
+        for (int i = lo; i < hi; i++)
+        {
+            double s = 0.0;
+            for (int j = A.ptr[i]; j < A.ptr[i + 1]; j++) s += A.val[j] * x[A.col[j]];
+            y[i] = s;
+        }
+    };
+    const int T = host_threads(A.num_rows);
+    if (T == 1) { rows(0, A.num_rows); return; }
+    std::vector<std::thread> pool; // rows are independent: same result for any T
+    for (int t = 0; t < T; t++) pool.emplace_back(rows, (int)((long long)A.num_rows * t / T), (int)((long long)A.num_rows * (t + 1) / T));
+    for (auto &th : pool) th.join();
 }
 
 // eigenvalues of a small dense symmetric matrix by cyclic Jacobi
@@ -540,17 +627,26 @@ class Hierarchy
             Level &L = levels.back();
             L.n = A.num_rows;
             L.A = std::move(A);
+            static const bool timing = getenv("PRFDD_AMG_TIMING") != nullptr;
+            auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+            double t0 = now();
             if (L.n > 0) cheby_setup(L.A, cheby_order, 1000 + (uint64_t)l, L.ds_hst, L.coefs, L.max_eig, L.min_eig);
+            double t1 = now();
             if (L.n <= max_coarse || l + 1 >= max_levels) break;
             std::vector<int> Sptr, Scol;
             strength(L.A, theta, Sptr, Scol);
+            double t2 = now();
             L.cf = pmis(L.n, Sptr, Scol, (uint64_t)l);
+            double t3 = now();
             int nc = 0;
             for (auto c : L.cf) nc += (c == 1);
             if (nc == 0 || nc == L.n) { L.cf.clear(); break; }
             L.P = interp_extpi(L.A, Sptr, Scol, L.cf, pmax);
+            double t4 = now();
             L.R = transpose(L.P);
             A = spgemm(spgemm(L.R, L.A), L.P);
+            double t5 = now();
+            if (timing) fprintf(stderr, "amg level %d rows %d: cheby %.2f strength %.2f pmis %.2f interp %.2f rap %.2f s\n", l, L.n, t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4);
             l++;
         }
         Ainv_hst = dense_inverse(levels.back().A);
