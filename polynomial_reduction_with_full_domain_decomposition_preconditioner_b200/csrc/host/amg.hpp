@@ -650,6 +650,7 @@ class Hierarchy
             l++;
         }
         Ainv_hst = dense_inverse(levels.back().A);
+        if (on_device) setup_mark("  AMG: coarsening, interpolation, Galerkin products (host)");
         if (on_device) upload();
     }
 
@@ -668,8 +669,10 @@ class Hierarchy
         }
         Ainv = device.malloc<double>(std::max<size_t>(Ainv_hst.size(), 1));
         Ainv.copyFrom(Ainv_hst.data(), Ainv_hst.size() * sizeof(double));
+        setup_mark("  AMG: upload");
         static const bool no_collapse = getenv("PRFDD_AMG_NO_COLLAPSE") != nullptr;
         if (!no_collapse) collapse(4096);
+        setup_mark("  AMG: collapsed coarse levels");
     }
 
     void collapse(int max_rows)

@@ -121,6 +121,7 @@ int prfdd_solver_create(prfdd_solver **out, const char *directory, const prfdd_o
         rstdout("- Superdomain overlap: \"%d\"\n", opt->superdomain_overlap);
         int N = opt->poly_degree;
         rstdout("\nSetting up domain \"N = %d\" object...\n", N);
+        setup_mark(nullptr);
         s->domains[N].reset(new Domain<STYPE>());
         s->domains[N]->num_vectors = opt->outer_num_vectors;
         s->domains[N]->initialize(directory, N, true);
@@ -141,6 +142,7 @@ int prfdd_solver_create(prfdd_solver **out, const char *directory, const prfdd_o
                 s->domains[level]->initialize(directory, level, false);
             }
             rstdout("Setting up subdomain object...\n");
+            setup_mark("Domain objects (reader, Q, halo lists)");
             s->subdomain.reset(new Subdomain<PTYPE>(s->domains, N, opt->poly_reduction, opt->subdomain_overlap, opt->superdomain_overlap, *opt));
         }
         else

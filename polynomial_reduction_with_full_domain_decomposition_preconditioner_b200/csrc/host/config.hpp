@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <iostream>
 #include <unordered_map>
 #include "device.hpp"
@@ -30,6 +31,19 @@ extern Timer<double> timer;
 extern Comm comm_world;      // stands where MPI_COMM_WORLD stands
 extern FILE *pstdout_file;
 } // namespace prfdd_host
+
+// set-up stopwatch: with PRFDD_SETUP_TIMING set, rank 0 prints the seconds since the previous mark (host wall clock; set-up is host work)
+inline void setup_mark(const char *what)
+{
+    static const bool on = getenv("PRFDD_SETUP_TIMING") != nullptr;
+    static double last = -1.0;
+    if (!on || prfdd_host::proc_id != 0) return;
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec + 1e-9 * ts.tv_nsec;
+    if (last >= 0.0 && what) fprintf(stderr, "[setup] %-44s %7.2f s\n", what, now - last);
+    last = now;
+}
 
 #define rstdout(...) { if (prfdd_host::proc_id == 0 && prfdd_host::verbose) { printf(__VA_ARGS__); fflush(stdout); } }
 #define pstdout(...) { if (prfdd_host::pstdout_file) { fprintf(prfdd_host::pstdout_file, __VA_ARGS__); fflush(prfdd_host::pstdout_file); } }

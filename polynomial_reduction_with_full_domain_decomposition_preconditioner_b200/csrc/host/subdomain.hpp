@@ -22,6 +22,8 @@
 // Status: num_procs == 1 (empty superdomain) is complete; the multi-rank region / superdomain
 // construction is in subdomain_multi.hpp.
 #pragma once
+#include <thread>
+#include <atomic>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -467,8 +469,11 @@ void Subdomain<DType>::build_single_rank(std::map<int, std::unique_ptr<Domain<DT
     rstdout("Assembling subdomain low-order preconditioner\n");
     if (use_preconditioner)
     {
+        setup_mark("region, Q, weights (1 rank)");
         assemble_low_order_fem();
+        setup_mark("low-order FEM assembly");
         amg_fem.setup(A_fem_hst, cheby_order);
+        setup_mark("AMG #2 (hierarchy, upload, collapsed coarse levels)");
     }
 }
 
@@ -507,11 +512,32 @@ void Subdomain<DType>::assemble_low_order_fem()
     std::vector<std::vector<std::pair<int, DType>>> rows(n_ext); // (col, value) in insertion order
 
     const int nslots = (dim == 2) ? 9 : 27;
+    // The elements are independent until their contributions are appended to the rows; the P1 simplex matrices (6 tetrahedra per
+    // GLL cell) dominate the set-up time.  Chunks of elements are processed by a few threads, each emitting (row, col, value)
+    // triplets in the serial order; the triplets are then appended chunk by chunk, so every row receives its entries in exactly
+    // the order of the serial loop and the assembled matrix is bit-identical for any thread count.
+    struct Trip
+    {
+        int row, col;
+        DType val;
+    };
+    const int num_region = (int)subdomain_region.size();
+    long long region_points = 0;
+    for (auto &el : subdomain_region) region_points += el.num_points;
+    const int T = amg::host_threads((int)std::min<long long>(region_points, 1 << 30));
+    const int nchunks = T == 1 ? 1 : std::min(num_region, 16 * T);
+    std::vector<std::vector<Trip>> emitted(std::max(nchunks, 1));
+    std::atomic<int> next_chunk(0);
+    auto worker = [&]() {
     std::vector<DType> Ae; // [point][slot], slot = neighbour offset (di,dj,dk) in {-1,0,1}^dim
     std::vector<char> touched;
-
-    for (auto &elem_i : subdomain_region)
+    for (int chunk = next_chunk++; chunk < nchunks; chunk = next_chunk++)
     {
+    std::vector<Trip> &out = emitted[chunk];
+    const int e_lo = (int)((long long)num_region * chunk / nchunks), e_hi = (int)((long long)num_region * (chunk + 1) / nchunks);
+    for (int e_idx = e_lo; e_idx < e_hi; e_idx++)
+    {
+        Element<DType> &elem_i = subdomain_region[e_idx];
         const int N_i = elem_i.poly_degree, n_i = N_i + 1;
         const int npts = elem_i.num_points;
         Ae.assign((size_t)npts * nslots, 0.0);
@@ -663,7 +689,7 @@ void Subdomain<DType>::assemble_low_order_fem()
                     if (!(std::abs(val) > epsilon)) continue;
                     const long long cb = elem_i.dof_num[slot_target(a, s)];
                     if (cb <= 0) continue;
-                    rows[ra - 1].push_back({(int)(cb - 1), val});
+                    out.push_back(Trip{(int)(ra - 1), (int)(cb - 1), val});
                 }
             }
             continue;
@@ -725,7 +751,7 @@ void Subdomain<DType>::assemble_low_order_fem()
             {
                 if (edge_cols[q].empty()) continue;
                 const int n_j = (int)edge_cols[q].size();
-                const std::vector<DType> &Jf = J_cf_fem[std::pair<int, int>(n_j - 1, N_i)];
+                const std::vector<DType> &Jf = J_cf_fem.at(std::pair<int, int>(n_j - 1, N_i));
                 for (auto &pr : edge_cols[q]) dcol[pr.first - 1] = pr.second;
                 for (int i = 1; i < n_i - 1; i++)
                     for (int j = 0; j < n_j; j++)
@@ -735,7 +761,7 @@ void Subdomain<DType>::assemble_low_order_fem()
             {
                 if (face_cols[q].empty()) continue;
                 const int n_j = (int)std::lround(std::sqrt((double)face_cols[q].size()));
-                const std::vector<DType> &Jf = J_cf_fem[std::pair<int, int>(n_j - 1, N_i)];
+                const std::vector<DType> &Jf = J_cf_fem.at(std::pair<int, int>(n_j - 1, N_i));
                 for (auto &pr : face_cols[q]) dcol[pr.first - 1] = pr.second;
                 for (int j = 1; j < n_i - 1; j++)
                     for (int i = 1; i < n_i - 1; i++)
@@ -762,10 +788,24 @@ void Subdomain<DType>::assemble_low_order_fem()
                 for (int cb = 0; cb < ncols; cb++)
                 {
                     const DType val = acc[(size_t)ca * ncols + cb];
-                    if (std::abs(val) > epsilon && dcol[cb] > 0) rows[dcol[ca] - 1].push_back({(int)(dcol[cb] - 1), val});
+                    if (std::abs(val) > epsilon && dcol[cb] > 0) out.push_back(Trip{(int)(dcol[ca] - 1), (int)(dcol[cb] - 1), val});
                 }
             }
         }
+    }
+    }
+    };
+    if (T == 1) worker();
+    else
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; t++) pool.emplace_back(worker);
+        for (auto &th : pool) th.join();
+    }
+    for (auto &chunk : emitted)
+    {
+        for (const Trip &t : chunk) rows[t.row].push_back({t.col, t.val});
+        std::vector<Trip>().swap(chunk);
     }
 
     // A_sub_fem rows -> composite A_fem through the interface numbering (tpp:3414-3472)

@@ -325,6 +325,7 @@ void Subdomain<DType>::build_multi_rank(std::map<int, std::unique_ptr<Domain<DTy
     }
 
     // ---- region Q with interpolation rows on non-conforming edges / faces (tpp:1496-1585) ------------
+    setup_mark("regions, rings, tree ids, renumbering");
     build_region_Q(subdomain_region, subdomain_operator.Q);
     build_region_Q(superdomain_region, superdomain_operator.Q);
     subdomain_operator.Q.transpose(subdomain_operator.Qt);
@@ -410,20 +411,27 @@ void Subdomain<DType>::build_multi_rank(std::map<int, std::unique_ptr<Domain<DTy
         A0 = csr_from_coo(num_coarse_dofs, num_coarse_dofs, coo);
     }
     // BoomerAMG #1 stand-in: coarsen to a single dof (tpp:1851-1858)
+    setup_mark("region Q, operators, global N=1 matrix");
     amg_coarse.setup(A0, 1, /*max_coarse=*/1, 0.25, 4, 25, /*on_device=*/false);
+    setup_mark("AMG #1 (global N=1 matrix)");
 
     build_superdomain(amg_coarse, sub_ids, sup_ids, interface_glo_num, glo_num_coarse, num_coarse_dofs);
+    setup_mark("composite superdomain grid");
     build_interface(sub_ids, sup_ids, subdomain_partition, (int)interface_glo_num.size());
+    setup_mark("interface maps, weights");
 
     // ---- low-order preconditioner (tpp:2749-3549) ------------------------------------------------------
     rstdout("Assembling subdomain low-order preconditioner\n");
     if (use_preconditioner)
     {
         assemble_low_order_fem();
+        setup_mark("low-order FEM assembly");
         amg_fem.setup(A_fem_hst, cheby_order);
+        setup_mark("AMG #2 (hierarchy, upload, collapsed coarse levels)");
     }
 
     setup_tree_exchange();
+    setup_mark("tree exchange lists");
 }
 
 // Q1 SEM element matrix D^T G D of an N = 1 element (tpp:1715-1826, 3040-3124); Ae row-major nv x nv
