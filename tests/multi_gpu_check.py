@@ -97,6 +97,15 @@ def main():
                   % (solver_id, gathered[0]["nit"], W.num_iterations, rel.max(), num / den), flush=True)
             assert rel.max() < (1e-8 if a.pc else 5e-2)
             assert num / den < (1e-10 if a.pc else 1e-6)
+            if a.pc:
+                # the same numbers computed by the oracle in the build container (tests/golden/solve_histories.json), if this case is there
+                import json
+                gold = [c for c in json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solve_histories.json")))
+                        if (c["dim"], c["nel"], c["N"], c["r"], c["eps"], c["ranks"], c["solver"]) == (a.dim, a.nel, a.N, a.r, a.eps, world, solver_id)]
+                for c in gold:
+                    ref = np.array(c["history"])
+                    assert gathered[0]["nit"] == c["iterations"] and np.abs(gathered[0]["hist"] - ref).max() <= 1e-9 * ref[0]
+                    print("golden history (build container) matched: %d iterations" % c["iterations"], flush=True)
     S.close()
     dist.barrier()
     if rank == 0:

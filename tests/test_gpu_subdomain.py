@@ -93,3 +93,25 @@ def test_preconditioned_parity(prfdd, tmp_path, dim, nel, N, r, eps):
     assert n1 == n2 and np.array_equal(h1, h2) and np.array_equal(S1.get_array("U"), S2.get_array("U"))
     assert S2.query("GPU_LAUNCHES_PER_PRECOND") > 0
     S1.close(); S2.close(); S.close()
+
+
+def _golden_cases():
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solve_histories.json")))
+    return [c for c in g if c["ranks"] == 1]
+
+
+@pytest.mark.parametrize("case", _golden_cases(), ids=lambda c: "%dd_nel%d_N%d_r%d_s%d" % (c["dim"], c["nel"], c["N"], c["r"], c["solver"]))
+def test_solve_matches_golden_history(prfdd, tmp_path, case):
+    """iteration count and residual history against tests/golden/solve_histories.json (the oracle's numbers computed in the build
+    container, tests/golden/make_solve_histories.py) -- independent of the oracle re-run on this machine"""
+    _need_gpu()
+    d = str(tmp_path)
+    prfdd.mesh_generate_box(d, case["dim"], case["nel"], case["N"], 1, case["eps"], reduction=case["r"])
+    S = prfdd.Solver(d, poly_degree=case["N"], poly_reduction=case["r"])
+    S.setup_problem(4)
+    nit, hist = S.solve(case["solver"])
+    ref = np.array(case["history"])
+    assert nit == case["iterations"] and len(hist) == len(ref)
+    assert np.abs(hist - ref).max() <= 1e-9 * ref[0]
+    S.close()
