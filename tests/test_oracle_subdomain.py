@@ -66,3 +66,22 @@ def test_regions_follow_the_ladder(tmp_path):
     assert S.num_superdomain_elems + S.num_subdomain_elems == 16 * 16
     # a 4-rank block of 8x8 own elements + 3 rings (clipped by the domain boundary) = 11x11
     assert S.num_subdomain_elems == 11 * 11 and S.num_subdomain_extended_elems == 12 * 12
+
+
+@pytest.mark.parametrize("dim,nel,N,r,nr", [(2, 8, 7, 3, 1), (3, 4, 4, 3, 1), (3, 4, 3, 2, 2)])
+def test_vcycle_contracts(tmp_path, dim, nel, N, r, nr):
+    """pin 5 of SURVEY 8c (the reference's own `#if 0` self-test, subdomain.tpp:3707-3855): one V-cycle of the low-order
+    hierarchy reduces the residual of A_fem x = b, and the stationary iteration x += V(b - A x) converges"""
+    W, Sd = _setup(str(tmp_path), dim, nel, N, r, nr, 0.02)
+    rng = np.random.default_rng(11)
+    for S in Sd.ranks:
+        A = S.A_fem
+        b = rng.standard_normal(A.shape[0])
+        x = np.zeros_like(b)
+        res = [np.linalg.norm(b)]
+        for _ in range(6):
+            x = x + S.amg.vcycle(b - A @ x, 1)
+            res.append(np.linalg.norm(b - A @ x))
+        rates = np.array(res[1:]) / np.array(res[:-1])
+        assert rates.max() < 0.6, rates
+        assert res[-1] / res[0] < 1e-3
