@@ -36,17 +36,15 @@ def time_level(A, name):
     r = torch.rand(nr, dtype=torch.float64, device="cuda"); ds = torch.rand(nr, dtype=torch.float64, device="cuda"); uu = torch.zeros(nr, dtype=torch.float64, device="cuda")
     gb = (12.0 * A.nnz + 4.0 * (nr + 1) + 8.0 * nr * 5) / 1e9
     out = []
-    flat = [-int(v) for v in os.environ.get("PRFDD_FLAT_R", "").split(",") if v]
     xh = x.cpu().numpy(); ref = A @ xh
-    caps = [int(v) for v in os.environ.get("PRFDD_CAPS", "").split(",") if v]
     t0 = tpr_of(A)
-    for tpr in sorted({1, t0, max(1, t0 // 2), min(32, t0 * 2)}) + flat + [t0 | (c << 8) for c in caps]:
+    for tpr in sorted({1, t0, max(1, t0 // 2), min(32, t0 * 2)}):
         L.prfdd_csr_multiply(P(y), P(ptr), P(col), P(val), P(x), C.c_int(nr), C.c_int(tpr), sh)
         torch.cuda.synchronize()
         err = np.abs(y.cpu().numpy() - ref).max() / np.abs(ref).max()
         assert err < 1e-13, (tpr, err)
         med, mn = timeit(lambda: L.prfdd_cheby_step(P(uu), P(y), P(ptr), P(col), P(val), P(x), P(r), P(ds), C.c_double(0.5), C.c_int(1), C.c_int(0), C.c_int(nr), C.c_int(tpr), sh))
-        out.append("tpr%d%s %.1fus (%.2f)" % (tpr & 255, "/cap%d" % (tpr >> 8) if tpr >> 8 else "", med * 1e3, gb / (med * 1e-3) / PEAK))
+        out.append("tpr%d %.1fus (%.2f)" % (tpr, med * 1e3, gb / (med * 1e-3) / PEAK))
     print("  %-14s rows %8d nnz/row %5.1f: %s" % (name, nr, A.nnz / nr, "  ".join(out)), flush=True)
 
 

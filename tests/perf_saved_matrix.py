@@ -20,7 +20,7 @@ rr = torch.rand(nr, dtype=torch.float64, device="cuda"); ds = torch.rand(nr, dty
 gb = (12.0 * A.nnz + 4.0 * (nr + 1) + 8.0 * nr * 5) / 1e9
 for arg in [int(v) for v in sys.argv[2:]] or [1]:
     t, _ = timeit_batch(lambda: L.prfdd_cheby_step(P(uu), P(y), P(ptr), P(col), P(val), P(x), P(rr), P(ds), C.c_double(0.5), C.c_int(1), C.c_int(0), C.c_int(nr), C.c_int(arg), sh), reps=5, warm=2)
-    print("tpr %d cap %d: %.1f us (%.2f)" % (arg & 255, arg >> 8, t * 1e3, gb / (t * 1e-3) / PEAK), flush=True)
+    print("tpr %d: %.1f us (%.2f)" % (arg, t * 1e3, gb / (t * 1e-3) / PEAK), flush=True)
 rl = np.diff(A.indptr)
 n = nr
 for arg in [int(v) for v in sys.argv[2:]] or [1]:
@@ -29,9 +29,6 @@ for arg in [int(v) for v in sys.argv[2:]] or [1]:
         lo, hi = q * n // 8, (q + 1) * n // 8 - 1
         t, _ = timeit_batch(lambda: L.prfdd_csr_multiply_range(P(y), P(ptr), P(col), P(val), P(x), C.c_int(lo), C.c_int(hi), C.c_int(arg), sh), reps=10, warm=2)
         out.append("%.1f" % (t * 1e3))
-    print("tpr %d cap %d eighths (us): %s" % (arg & 255, arg >> 8, " ".join(out)), flush=True)
+    print("tpr %d eighths (us): %s" % (arg, " ".join(out)), flush=True)
 print("max row length per eighth:", [int(rl[q * n // 8:(q + 1) * n // 8].max()) for q in range(8)])
 print("rows > 16 per eighth:", [int((rl[q * n // 8:(q + 1) * n // 8] > 16).sum()) for q in range(8)])
-cd = np.abs(A.indices - np.repeat(np.arange(n), rl))
-print("median |col-row| per eighth:", [int(np.median(cd[A.indptr[q * n // 8]:A.indptr[(q + 1) * n // 8]])) for q in range(8)])
-print("p90 |col-row| per eighth:", [int(np.percentile(cd[A.indptr[q * n // 8]:A.indptr[(q + 1) * n // 8]], 90)) for q in range(8)])
