@@ -243,30 +243,35 @@ inline std::vector<signed char> pmis(int n, const std::vector<int> &Sptr, const 
         if (count[i] == 0) { cf[i] = -1; und[i] = 0; }
         else remaining++;
     }
-    std::vector<char> newc(n);
+    // sweeps over the still undecided nodes only (ascending index, as a full sweep would visit them)
+    std::vector<int> active, winners, still;
+    active.reserve(remaining);
+    for (int i = 0; i < n; i++)
+        if (und[i]) active.push_back(i);
     while (remaining > 0)
     {
         // local maxima of the rank among undecided neighbours in S + S^T (decided from the state at sweep start)
-        for (int i = 0; i < n; i++)
+        winners.clear();
+        for (int i : active)
         {
-            newc[i] = 0;
-            if (!und[i]) continue;
             int mx = -1;
             for (int j = Sptr[i]; j < Sptr[i + 1]; j++)
                 if (und[Scol[j]]) mx = std::max(mx, rank[Scol[j]]);
             for (int j = Tptr[i]; j < Tptr[i + 1]; j++)
                 if (und[Tcol[j]]) mx = std::max(mx, rank[Tcol[j]]);
-            if (rank[i] > mx) newc[i] = 1;
+            if (rank[i] > mx) winners.push_back(i);
         }
-        for (int i = 0; i < n; i++)
-            if (newc[i]) { cf[i] = 1; und[i] = 0; remaining--; }
-        for (int i = 0; i < n; i++)
+        for (int i : winners) { cf[i] = 1; und[i] = 0; remaining--; }
+        still.clear();
+        for (int i : active)
         {
             if (!und[i]) continue;
             bool hit = false;
             for (int j = Sptr[i]; j < Sptr[i + 1] && !hit; j++) hit = (cf[Scol[j]] == 1);
             if (hit) { cf[i] = -1; und[i] = 0; remaining--; }
+            else still.push_back(i);
         }
+        active.swap(still);
     }
     return cf;
 }
