@@ -389,6 +389,13 @@ int prfdd_solver_apply(prfdd_solver *s, int what, const double *in_host, double 
  * events on the solver's stream.  out[0] = average ms per launch, out[1] = average algorithmic bytes per launch
  * (12*nnz + 4*(rows+1) + 5*8*rows), out[2] = rows of level 0, out[3] = nnz of level 0, out[4] = rows of level 1, out[5] = nnz of level 1 */
 int prfdd_solver_time_spmv(prfdd_solver *s, int reps, double out[6]);
+/* field output (Domain::output, domain.tpp:373-524; the reference writes Silo, compiled out by VISUALIZATION 0): the low-order
+ * cell mesh (every GLL cell a quad / hexahedron) with node-centred fields as a legacy-VTK unstructured grid.  Host arrays,
+ * element-major points, n = points per direction. */
+int prfdd_write_vtk(const char *path, int dim, int n, int num_elements, const double *x, const double *y, const double *z, int num_fields,
+                    const char *const *field_names, const double *const *fields);
+/* poisson.cpp:233-235: u_star, f, u of this rank's elements -> <output_name>_<rank>.vtk */
+int prfdd_solver_output(prfdd_solver *s, const char *output_name);
 /* timer report (Timer keys of timer.tpp / poisson.cpp:253-401): seconds for `key`, <0 if unknown */
 double prfdd_solver_timer_total(prfdd_solver *s, const char *key);
 

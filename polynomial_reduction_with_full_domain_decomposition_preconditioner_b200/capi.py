@@ -147,5 +147,9 @@ class Solver:
         check(lib().prfdd_solver_apply(self.h, C.c_int(APPLY[what]), x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)), "apply " + what)
         return out
 
+    def output(self, name):
+        """u_star, f, u of this rank's elements -> <name>_<rank>.vtk (poisson.cpp:233-235)"""
+        check(lib().prfdd_solver_output(self.h, name.encode()), "output")
+
     def timer(self, key):
         return float(lib().prfdd_solver_timer_total(self.h, key.encode()))

@@ -389,6 +389,32 @@ int prfdd_amg_host_get_coarse_inverse(const prfdd_amg_host *h, double *Ainv)
     return 0;
 }
 
+int prfdd_solver_output(prfdd_solver *s, const char *output_name)
+{
+    // poisson.cpp:233-235: domain.output("domain", 3, "u_star", u_star, "f", f, "u", u); one piece per rank here
+    return guarded(s, [&]() {
+        Domain<STYPE> *d = s->domain;
+        const long long P = d->num_local_points;
+        std::vector<double> x(P), y(P), z(P), us(P), ff(P), uu(P);
+        long long at = 0;
+        for (auto &e : d->elements)
+            for (size_t v = 0; v < e.x.size(); v++, at++)
+            {
+                x[at] = e.x[v];
+                y[at] = e.y.empty() ? 0.0 : e.y[v];
+                z[at] = e.z.empty() ? 0.0 : e.z[v];
+            }
+        s->u_star.copyTo(us.data(), P * sizeof(double));
+        s->f.copyTo(ff.data(), P * sizeof(double));
+        s->u.copyTo(uu.data(), P * sizeof(double));
+        char path[1024];
+        snprintf(path, sizeof(path), "%s_%d.vtk", output_name, prfdd_host::proc_id);
+        const char *names[3] = {"u_star", "f", "u"};
+        const double *fields[3] = {us.data(), ff.data(), uu.data()};
+        return prfdd_write_vtk(path, prfdd_host::dim, d->poly_degree + 1, d->num_local_elements, x.data(), y.data(), z.data(), 3, names, fields);
+    });
+}
+
 double prfdd_solver_timer_total(prfdd_solver *s, const char *key)
 {
     if (!strcmp(key, "__enable__")) { s->tmr.enabled = true; return 0.0; }

@@ -1,5 +1,6 @@
 // globals.cpp -- definitions of the process-wide globals of config.hpp and the small library-level
 // C ABI (version, device selection, buffers).
+#include <cstdio>
 #include "config.hpp"
 #include "../../../include/prfdd_b200.h"
 #include <algorithm>
@@ -82,5 +83,47 @@ int prfdd_memcpy_h2d(void *dst, const void *src, size_t bytes, prfdd_stream_t s)
 int prfdd_memcpy_d2h(void *dst, const void *src, size_t bytes, prfdd_stream_t s) { return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)s); }
 int prfdd_memcpy_d2d(void *dst, const void *src, size_t bytes, prfdd_stream_t s) { return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)s); }
 int prfdd_stream_synchronize(prfdd_stream_t s) { return (int)cudaStreamSynchronize((cudaStream_t)s); }
+
+// Field output (Domain::output, domain.tpp:373-524; Subdomain::output, subdomain.tpp:4648-4791): the reference writes one Silo
+// file (UCD mesh of the low-order cells, every GLL cell a quad / hexahedron, node-centred fields).  Silo is not available; the
+// same mesh and fields go to a legacy-VTK unstructured grid (cell types 9 / 12 have the reference's vertex order), readable by
+// VisIt and ParaView.  Host arrays, element-major points.
+int prfdd_write_vtk(const char *path, int dim, int n, int num_elements, const double *x, const double *y, const double *z, int num_fields,
+                    const char *const *field_names, const double *const *fields)
+{
+    if (!path || (dim != 2 && dim != 3) || n < 2 || num_elements < 0 || !x || !y || (dim == 3 && !z)) return -8;
+    FILE *f = fopen(path, "w");
+    if (!f) return -2;
+    const long long npe = (dim == 2) ? (long long)n * n : (long long)n * n * n;
+    const long long num_points = npe * num_elements;
+    const int nv = (dim == 2) ? 4 : 8;
+    const long long cells_per_elem = (dim == 2) ? (long long)(n - 1) * (n - 1) : (long long)(n - 1) * (n - 1) * (n - 1);
+    const long long num_cells = cells_per_elem * num_elements;
+    fprintf(f, "# vtk DataFile Version 3.0\nField data\nASCII\nDATASET UNSTRUCTURED_GRID\nPOINTS %lld double\n", num_points);
+    for (long long p = 0; p < num_points; p++) fprintf(f, "%.17g %.17g %.17g\n", x[p], y[p], dim == 3 ? z[p] : 0.0);
+    fprintf(f, "CELLS %lld %lld\n", num_cells, num_cells * (nv + 1));
+    for (int e = 0; e < num_elements; e++)
+        for (int sz = 0; sz < (dim == 3 ? n - 1 : 1); sz++)
+            for (int sy = 0; sy < n - 1; sy++)
+                for (int sx = 0; sx < n - 1; sx++)
+                {
+                    const long long b = e * npe + sx + (long long)sy * n + (long long)sz * n * n;
+                    if (dim == 2) fprintf(f, "4 %lld %lld %lld %lld\n", b, b + 1, b + 1 + n, b + n);
+                    else
+                    {
+                        const long long t = b + (long long)n * n;
+                        fprintf(f, "8 %lld %lld %lld %lld %lld %lld %lld %lld\n", b, b + 1, b + 1 + n, b + n, t, t + 1, t + 1 + n, t + n);
+                    }
+                }
+    fprintf(f, "CELL_TYPES %lld\n", num_cells);
+    for (long long c = 0; c < num_cells; c++) fprintf(f, dim == 2 ? "9\n" : "12\n");
+    if (num_fields > 0) fprintf(f, "POINT_DATA %lld\n", num_points);
+    for (int k = 0; k < num_fields; k++)
+    {
+        fprintf(f, "SCALARS %s double 1\nLOOKUP_TABLE default\n", field_names[k]);
+        for (long long p = 0; p < num_points; p++) fprintf(f, "%.17g\n", fields[k][p]);
+    }
+    return fclose(f) == 0 ? 0 : -2;
+}
 
 } // extern "C"

@@ -89,6 +89,11 @@ int main(int argc, char *argv[])
     std::vector<double> hist(2048);
     rc = prfdd_solver_solve(s, solver_id, &iters, hist.data(), (int)hist.size(), &hl);
     if (rc) { printf("ERROR: %s\n", prfdd_error_string(rc)); return EXIT_FAILURE; }
+    if (getenv("PRFDD_OUTPUT")) // poisson.cpp:233-235 (VISUALIZATION): u_star, f, u -> <name>_<rank>.vtk
+    {
+        rc = prfdd_solver_output(s, getenv("PRFDD_OUTPUT"));
+        if (rc) { printf("ERROR: %s\n", prfdd_error_string(rc)); return EXIT_FAILURE; }
+    }
     if (opt.proc_id == 0)
     {
         printf("\nRun info:\n-------------------------------------------------------------------------\n");

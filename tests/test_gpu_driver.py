@@ -22,7 +22,7 @@ def test_poisson_driver(prfdd, tmp_path, solver_id):
     assert os.path.exists(BINARY), "driver binary missing: run __graft_entry__.build()"
     d = str(tmp_path)
     prfdd.mesh_generate_box(d, 3, 3, 4, 1, 0.03, reduction=3)
-    env = dict(os.environ, PRFDD_TIMINGS="1", PRFDD_TOLERANCE="1e-8")
+    env = dict(os.environ, PRFDD_TIMINGS="1", PRFDD_TOLERANCE="1e-8", PRFDD_OUTPUT=os.path.join(d, "domain"))
     out = subprocess.run([BINARY, d, "4", "3", "1", "0", str(solver_id)], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     W = odomain.DomainWorld(d, 4, 1)
@@ -41,6 +41,11 @@ def test_poisson_driver(prfdd, tmp_path, solver_id):
         assert re.search(r"^%s\s+=\s+[0-9.]+ s" % row, out.stdout, re.M), (row, out.stdout)
     total = float(re.search(r"^Total\s+=\s+([0-9.]+) s", out.stdout, re.M).group(1))
     assert total > 0.0
+    # field output (u_star, f, u on the low-order cell mesh): 27 elements of 5^3 points, 4^3 cells each
+    head = open(os.path.join(d, "domain_0.vtk")).read(400)
+    assert "DATASET UNSTRUCTURED_GRID" in head and "POINTS %d double" % (27 * 125) in head
+    text = open(os.path.join(d, "domain_0.vtk")).read()
+    assert "CELLS %d %d" % (27 * 64, 27 * 64 * 9) in text and all(("SCALARS %s double 1" % k) in text for k in ("u_star", "f", "u"))
 
 
 def test_usage_message():
