@@ -107,12 +107,53 @@ int prfdd_scatter_assign(double *dst, const double *buf, const int *idx, int cou
  * shuffle reduction); 0 = library default.  Callers pick it from nnz/rows of the matrix.
  * Row-indexed arguments may be offset to run a range of rows with its own hint (ptr + r0, outputs + r0; col, val and the
  * gathered vector unshifted). */
-/* Long rows: a thread (or sub-warp) that walks a row many times the average length alone outlasts the rest of the kernel.
- * A matrix may register the device list of its rows longer than `threshold` entries, keyed by the device address of its
- * row-pointer array; every SpMV of this family called with that `ptr` (whole matrix, not a row range) then leaves those
- * rows to a second launch that gives each a whole warp.  count = 0 clears the registration; call it whenever a row-pointer
- * array is (re)uploaded so that a recycled address cannot keep a stale list.  Host-side state of the calling process. */
-int prfdd_csr_set_long_rows(const int *ptr, const int *long_rows, int count, int threshold);
+/* Matrix descriptor: the CSR arrays plus the launch plan of the matrix.  It replaces the process-global registration of
+ * round 1 (a list keyed by the device address of `ptr`): everything a launch needs travels in the call.
+ *   val == NULL   every stored value is 1.0 (Q and Q^T of a conforming region, domain.tpp:286-294): the value stream is
+ *                 never read;
+ *   ptr == NULL   exactly one entry per row, row i holds entry i (Q of a conforming region): index-map kernel;
+ *   long_rows     device list of the rows longer than long_row_threshold entries: the row kernels skip them and a second
+ *                 launch gives each a whole warp (hanging-node rows of the composite grid); optional;
+ *   stage_cap     > 0: the warp-staged kernel may be used -- a warp copies the contiguous col/val slice of
+ *                 (32 / threads_per_row) * stage_rows_per_lane_group consecutive rows to shared memory with cp.async
+ *                 (double-buffered) and walks the rows from there; stage_cap = entries per buffer (multiple of 32),
+ *                 groups with a longer slice read global memory directly.
+ * prfdd_csr_plan fills the plan from the HOST copy of ptr.  A descriptor is plain data: copy it freely, keep the device
+ * arrays alive while it is in use. */
+typedef struct prfdd_csr_matrix
+{
+    const int *ptr;
+    const int *col;
+    const double *val;
+    int num_rows;
+    int num_nnz;
+    int threads_per_row;
+    const int *long_rows;
+    int num_long_rows;
+    int long_row_threshold;
+    int stage_rows_per_lane_group;
+    int stage_cap;
+} prfdd_csr_matrix;
+/* host-side planning: sets threads_per_row, stage_rows_per_lane_group, stage_cap and long_row_threshold of *A from
+ * ptr_host[0..num_rows] (A->num_rows must be set; A->num_nnz is set to ptr_host[num_rows]).  The rows longer than the
+ * threshold are written to long_rows_host (capacity entries) and their count is returned (0: no list needed; the caller
+ * uploads the list and sets A->long_rows / A->num_long_rows).  Returns -(count) if the capacity is too small. */
+int prfdd_csr_plan(prfdd_csr_matrix *A, const int *ptr_host, int *long_rows_host, int capacity);
+/* 0: row-group kernels only, 1: warp-staged kernels where the descriptor carries a plan (default; env PRFDD_SPMV_VARIANT);
+ * ctas_per_sm > 0 caps the residency of the staged kernel (measurement aid) */
+int prfdd_csr_set_spmv_variant(int variant, int ctas_per_sm);
+/* descriptor forms of the entry points below (same arithmetic, same epilogues) */
+int prfdd_csrm_multiply(double *Au, const prfdd_csr_matrix *A, const double *u, prfdd_stream_t stream);
+int prfdd_csrm_multiply_range(double *Au, const prfdd_csr_matrix *A, const double *u, int row_start, int row_end, prfdd_stream_t stream);
+int prfdd_csrm_multiply_weight(double *Au, const prfdd_csr_matrix *A, const double *u, const double *weight, prfdd_stream_t stream);
+int prfdd_csrm_matvec(double *y, const prfdd_csr_matrix *A, const double *x, double alpha, double beta, prfdd_stream_t stream);
+int prfdd_csrm_residual(double *v, const prfdd_csr_matrix *A, const double *u, const double *f, prfdd_stream_t stream);
+int prfdd_csrm_cheby_residual(double *r, double *t, const prfdd_csr_matrix *A, const double *u, const double *f, const double *ds,
+                              double c_hi, prfdd_stream_t stream);
+int prfdd_csrm_restrict_cheby_residual(double *f, double *r, double *t, const prfdd_csr_matrix *R, const double *v, const double *ds,
+                                       double c_hi, prfdd_stream_t stream);
+int prfdd_csrm_cheby_step(double *u, double *t_out, const prfdd_csr_matrix *A, const double *t_in, const double *r, const double *ds,
+                          double c, int last, int u_is_zero, prfdd_stream_t stream);
 /* y = A x                                        CSR_Matrix::multiply       csr_matrix.okl:5-18 */
 int prfdd_csr_multiply(double *Au, const int *ptr, const int *col, const double *val, const double *u,
                        int num_rows, int threads_per_row, prfdd_stream_t stream);
@@ -226,6 +267,16 @@ int prfdd_weighted_inner_product(prfdd_reduce_ws *ws, double *out, const double 
  *                                                  pass (subdomain.tpp:4389-4394, domain.tpp:810-815) */
 int prfdd_multi_inner_product(prfdd_reduce_ws *ws, double *out, const double *u, const double *const *V,
                               const double *w, int count, int n, prfdd_stream_t stream);
+/* fused Arnoldi column of the rank-local GMRES (Subdomain::generalized_minimum_residual, subdomain.tpp:4389-4458), working on the
+ * assembled copies aV_k = Q^T V_k that are kept from the previous steps (Q^T is linear):
+ *   prfdd_orthogonalize_norm   aq <- aq - sum_k coef[k] aV_k ;  out[0] = sum_i w[i] aq[i]^2
+ *   prfdd_arnoldi_next         V_next = scale (q - sum_k coef[k] V_k)  (n entries);  aV_next = scale aq  (n_assembled entries)
+ * coef, scale and out live in device memory; count <= 32.  They replace the reference's j+1 vector_vector_addition launches, the
+ * second assembly + residual_norm of the orthogonalised column and the two vector_scaling launches. */
+int prfdd_orthogonalize_norm(prfdd_reduce_ws *ws, double *out, double *aq, const double *const *aV, const double *coef, const double *w,
+                             int count, int n, prfdd_stream_t stream);
+int prfdd_arnoldi_next(double *V_next, const double *q, const double *const *V, const double *coef, int count, const double *scale, int n,
+                       double *aV_next, const double *aq, int n_assembled, prfdd_stream_t stream);
 /* out[0] = sum z*r*w ; out[1] = sum p*q*w          projection_inner_products subdomain.okl:165-209 */
 int prfdd_weighted_projection_inner_products(prfdd_reduce_ws *ws, double *out, const double *z_k, const double *r_k,
                                              const double *p_k, const double *q_k, const double *weight, int n,

@@ -571,13 +571,11 @@ inline std::vector<double> dense_inverse(const HostCSR &A)
     return I;
 }
 
-// lanes per row from the average row length (measured on B200, profiles/r1_spmv_tpr.txt and r1_notes.txt)
-inline int lanes_per_row(double avg, int num_rows) { return avg <= 10 ? 1 : avg <= 18 ? 2 : (avg > 60 && num_rows < 50000) ? 16 : 8; }
-
 struct DeviceCSR
 {
     int num_rows = 0, num_cols = 0, nnz = 0, tpr = 4;
     dev::memory ptr, col, val, long_rows;
+    prfdd_csr_matrix desc = {}; // device arrays + launch plan, as the C ABI takes them
     void upload(const HostCSR &A)
     {
         num_rows = A.num_rows; num_cols = A.num_cols; nnz = A.nnz();
@@ -587,9 +585,11 @@ struct DeviceCSR
         ptr.copyFrom(A.ptr.data(), (num_rows + 1) * sizeof(int));
         col.copyFrom(A.col.data(), nnz * sizeof(int));
         val.copyFrom(A.val.data(), nnz * sizeof(double));
-        const double avg = (double)nnz / std::max(num_rows, 1);
-        tpr = lanes_per_row(avg, num_rows);
-        long_rows = ::register_long_rows(ptr.as<int>(), A.ptr.data(), num_rows, avg, tpr);
+        desc = prfdd_csr_matrix();
+        desc.ptr = ptr.as<int>(); desc.col = col.as<int>(); desc.val = val.as<double>();
+        desc.num_rows = num_rows;
+        long_rows = ::plan_csr(desc, A.ptr.data());
+        tpr = desc.threads_per_row;
     }
 };
 
@@ -716,10 +716,9 @@ class Hierarchy
         cudaStream_t st = prfdd_host::device.stream;
         const int k = cheby_order;
         double *u = L.u.as<double>(), *r = L.r.as<double>(), *t0 = L.t0.as<double>(), *t1 = L.t1.as<double>();
-        const int *ptr = L.dA.ptr.as<int>(), *col = L.dA.col.as<int>();
-        const double *val = L.dA.val.as<double>(), *ds = L.ds.as<double>(), *f = L.f.as<double>();
+        const double *ds = L.ds.as<double>(), *f = L.f.as<double>();
         // residual_done: the restriction that produced f already wrote r and t0 (prfdd_restrict_cheby_residual)
-        if (!residual_done) dev::check_rc(prfdd_cheby_residual(r, t0, ptr, col, val, u_is_zero ? nullptr : u, f, ds, L.coefs[k - 1], L.n, L.dA.tpr, st), "cheby_residual");
+        if (!residual_done) dev::check_rc(prfdd_csrm_cheby_residual(r, t0, &L.dA.desc, u_is_zero ? nullptr : u, f, ds, L.coefs[k - 1], st), "cheby_residual");
         if (k == 1)
         {
             dev::check_rc(prfdd_cheby_order1(u, r, ds, L.coefs[0], u_is_zero ? 1 : 0, L.n, st), "cheby_order1");
@@ -728,7 +727,7 @@ class Hierarchy
         double *tin = t0, *tout = t1;
         for (int p = k - 2; p >= 0; p--)
         {
-            dev::check_rc(prfdd_cheby_step(u, tout, ptr, col, val, tin, r, ds, L.coefs[p], p == 0 ? 1 : 0, u_is_zero ? 1 : 0, L.n, L.dA.tpr, st), "cheby_step");
+            dev::check_rc(prfdd_csrm_cheby_step(u, tout, &L.dA.desc, tin, r, ds, L.coefs[p], p == 0 ? 1 : 0, u_is_zero ? 1 : 0, st), "cheby_step");
             std::swap(tin, tout);
         }
     }
@@ -743,13 +742,13 @@ class Hierarchy
         {
             Level &L = levels[l];
             smooth(L, l > l0 || first_guess_is_zero, l > l0);
-            dev::check_rc(prfdd_csr_residual(L.v.as<double>(), L.dA.ptr.as<int>(), L.dA.col.as<int>(), L.dA.val.as<double>(), L.u.as<double>(), L.f.as<double>(), L.n, L.dA.tpr, st), "csr_residual");
+            dev::check_rc(prfdd_csrm_residual(L.v.as<double>(), &L.dA.desc, L.u.as<double>(), L.f.as<double>(), st), "csr_residual");
             Level &Lc = levels[l + 1];
             if (l + 1 < bottom) // the coarse level is smoothed next: fuse the head of that smoothing into the restriction
-                dev::check_rc(prfdd_restrict_cheby_residual(Lc.f.as<double>(), Lc.r.as<double>(), Lc.t0.as<double>(), L.dR.ptr.as<int>(), L.dR.col.as<int>(), L.dR.val.as<double>(), L.v.as<double>(),
-                                                            Lc.ds.as<double>(), Lc.coefs[cheby_order - 1], Lc.n, L.dR.tpr, st), "restrict + residual");
+                dev::check_rc(prfdd_csrm_restrict_cheby_residual(Lc.f.as<double>(), Lc.r.as<double>(), Lc.t0.as<double>(), &L.dR.desc, L.v.as<double>(),
+                                                                 Lc.ds.as<double>(), Lc.coefs[cheby_order - 1], st), "restrict + residual");
             else
-                dev::check_rc(prfdd_csr_multiply(Lc.f.as<double>(), L.dR.ptr.as<int>(), L.dR.col.as<int>(), L.dR.val.as<double>(), L.v.as<double>(), Lc.n, L.dR.tpr, st), "restrict");
+                dev::check_rc(prfdd_csrm_multiply(Lc.f.as<double>(), &L.dR.desc, L.v.as<double>(), st), "restrict");
         }
         Level &last = levels[bottom];
         if (bottom == nl - 1) dev::check_rc(prfdd_dense_solve(last.u.as<double>(), Ainv.as<double>(), last.f.as<double>(), last.n, st), "dense_solve");
@@ -758,7 +757,7 @@ class Hierarchy
         {
             Level &L = levels[l - 1];
             Level &Lc = levels[l];
-            dev::check_rc(prfdd_csr_matvec(L.u.as<double>(), L.dP.ptr.as<int>(), L.dP.col.as<int>(), L.dP.val.as<double>(), Lc.u.as<double>(), 1.0, 1.0, L.n, L.dP.tpr, st), "prolong");
+            dev::check_rc(prfdd_csrm_matvec(L.u.as<double>(), &L.dP.desc, Lc.u.as<double>(), 1.0, 1.0, st), "prolong");
             smooth(L, false);
         }
     }

@@ -14,36 +14,28 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <stdexcept>
 #include <tuple>
 #include <typeinfo>
 #include <vector>
 #include "config.hpp"
 #include "../../../include/prfdd_b200.h"
 
-// rows much longer than the average (and than the lanes that walk them can absorb) go to the warp-per-row launch
-// (prfdd_csr_set_long_rows); returns the device list that must stay alive with the matrix
-inline dev::memory register_long_rows(const int *ptr_dev, const int *ptr_hst, int num_rows, double avg, int tpr)
+// fills the launch plan of a descriptor from the host copy of the row pointers (prfdd_csr_plan) and uploads the list of
+// long rows, which must stay alive with the matrix
+inline dev::memory plan_csr(prfdd_csr_matrix &desc, const int *ptr_hst)
 {
-    static const bool off = getenv("PRFDD_SPMV_NO_LONG_ROWS") != nullptr;
-    const int threshold = std::max(std::max(16, 4 * tpr), (int)std::ceil(3.0 * avg));
-    std::vector<int> rows;
-    int longest = 0;
-    for (int r = 0; r < num_rows && !off; r++)
-    {
-        const int len = ptr_hst[r + 1] - ptr_hst[r];
-        longest = std::max(longest, len);
-        if (len > threshold) rows.push_back(r);
-    }
+    std::vector<int> rows((size_t)std::max(desc.num_rows / 20 + 1, 1));
+    int count = prfdd_csr_plan(&desc, ptr_hst, rows.data(), (int)rows.size());
+    if (count < 0) throw std::runtime_error("plan_csr: prfdd_csr_plan failed");
     dev::memory list;
-    // worth a second launch only when some row is several times the threshold (the tail it removes is then longer than the launch)
-    if (rows.empty() || tpr >= 32 || longest < 4 * threshold || (double)rows.size() > 0.05 * num_rows)
+    if (count > 0)
     {
-        prfdd_csr_set_long_rows(ptr_dev, nullptr, 0, 0);
-        return list;
+        list = prfdd_host::device.malloc<int>(count);
+        list.copyFrom(rows.data(), count * sizeof(int));
+        desc.long_rows = list.as<int>();
+        desc.num_long_rows = count;
     }
-    list = prfdd_host::device.malloc<int>(rows.size());
-    list.copyFrom(rows.data(), rows.size() * sizeof(int));
-    prfdd_csr_set_long_rows(ptr_dev, list.as<int>(), (int)rows.size(), threshold);
     return list;
 }
 
@@ -77,7 +69,10 @@ class CSR_Matrix
     std::vector<int> col_hst;
     std::vector<DType> val_hst;
     int threads_per_row = 1;
-    dev::memory long_rows; // rows given a whole warp (prfdd_csr_set_long_rows)
+    dev::memory long_rows;         // rows given a whole warp
+    prfdd_csr_matrix desc = {};    // device arrays + launch plan, as the C ABI takes them
+    bool unit_values = false;      // every stored value is 1.0: the value stream is never read (Q, Q^T of a conforming region)
+    bool one_entry_per_row = false; // row i holds exactly entry i: applied as an index map
 
     CSR_Matrix() {}
     CSR_Matrix(int num_rows_, int num_cols_) { initialize(num_rows_, num_cols_); }
@@ -159,9 +154,18 @@ class CSR_Matrix
         ptr.copyFrom(ptr_hst.data(), (num_rows + 1) * sizeof(int));
         col.copyFrom(col_hst.data(), num_nnz * sizeof(int));
         val.copyFrom(val_hst.data(), num_nnz * sizeof(DType));
-        double avg = (double)num_nnz / (double)std::max(num_rows, 1);
-        threads_per_row = avg <= 10 ? 1 : avg <= 18 ? 2 : (avg > 60 && num_rows < 50000) ? 16 : 8; // measured on B200, profiles/r1_spmv_tpr.txt and r1_notes.txt
-        long_rows = register_long_rows(ptr.as<int>(), ptr_hst.data(), num_rows, avg, threads_per_row);
+        desc = prfdd_csr_matrix();
+        desc.ptr = ptr.as<int>(); desc.col = col.as<int>(); desc.val = (const double *)val.ptr();
+        desc.num_rows = num_rows;
+        long_rows = plan_csr(desc, ptr_hst.data());
+        threads_per_row = desc.threads_per_row;
+        static const bool no_unit = getenv("PRFDD_CSR_NO_UNIT") != nullptr;
+        unit_values = !no_unit && typeid(DType) == typeid(double) && desc.stage_cap > 0;
+        for (int j = 0; j < num_nnz && unit_values; j++) unit_values = (val_hst[j] == (DType)1);
+        one_entry_per_row = unit_values && num_nnz == num_rows;
+        for (int i = 0; i <= num_rows && one_entry_per_row; i++) one_entry_per_row = (ptr_hst[i] == i);
+        if (unit_values) desc.val = nullptr;
+        if (one_entry_per_row) desc.ptr = nullptr;
     }
 
     void print(FILE *file_ptr = NULL, int offset = 0)
@@ -201,7 +205,7 @@ class CSR_Matrix
         if ((num_rows == 0) or (num_cols == 0)) return;
         initialization_check();
         if (num_nnz == 0) { dev::check_rc(prfdd_set_to_value(Au.as<double>(), 0.0, num_rows, 0, prfdd_host::device.stream), "CSR_Matrix::multiply"); return; }
-        dev::check_rc(prfdd_csr_multiply(Au.as<double>(), ptr.as<int>(), col.as<int>(), val.as<double>(), u.as<double>(), num_rows, threads_per_row, prfdd_host::device.stream), "CSR_Matrix::multiply");
+        dev::check_rc(prfdd_csrm_multiply(Au.as<double>(), &desc, u.as<double>(), prfdd_host::device.stream), "CSR_Matrix::multiply");
     }
 
     void multiply_range(const dev::memory &Au, const dev::memory &u, int row_start, int row_end)
@@ -221,6 +225,6 @@ class CSR_Matrix
         if ((num_rows == 0) or (num_cols == 0)) return;
         initialization_check();
         if (num_nnz == 0) { dev::check_rc(prfdd_set_to_value(Au.as<double>(), 0.0, num_rows, 0, prfdd_host::device.stream), "CSR_Matrix::multiply_weight"); return; }
-        dev::check_rc(prfdd_csr_multiply_weight(Au.as<double>(), ptr.as<int>(), col.as<int>(), val.as<double>(), u.as<double>(), weight.as<double>(), num_rows, threads_per_row, prfdd_host::device.stream), "CSR_Matrix::multiply_weight");
+        dev::check_rc(prfdd_csrm_multiply_weight(Au.as<double>(), &desc, u.as<double>(), weight.as<double>(), prfdd_host::device.stream), "CSR_Matrix::multiply_weight");
     }
 };

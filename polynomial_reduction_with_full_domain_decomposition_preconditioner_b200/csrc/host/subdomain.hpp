@@ -182,8 +182,9 @@ class Subdomain
     void ranking(std::vector<DType> &data, int size);
 
     void tree_operator(const memory &Tu, const memory &u);
-    void low_order_preconditioner(const memory &z, const memory &r);
+    void low_order_preconditioner(const memory &z, const memory &r, const memory *r_assembled = nullptr);
     void assemble_weighted(const memory &dst, const memory &src);
+    void assemble(const memory &dst, const memory &src);
     void residual_norm_dev(const memory &r, double *out);
     void gmres_body(const memory &u_l, const memory &f_l);
     void fcg_body(const memory &u_l, const memory &f_l);
@@ -908,33 +909,45 @@ void Subdomain<DType>::direct_stiffness_summation(const memory &QQtu, const memo
 }
 
 template <typename DType>
-void Subdomain<DType>::low_order_preconditioner(const memory &z, const memory &r)
+void Subdomain<DType>::low_order_preconditioner(const memory &z, const memory &r, const memory *r_assembled)
 {
     using namespace prfdd_host;
     // subdomain.tpp:3987-4159: z = Q Q_int Vcycle(A_fem) Qt_int Qt r
+    // r_assembled: [Qt r_sub | r_sup] when the caller already holds it (the Arnoldi loop keeps the assembled copy of every
+    // basis vector for its inner products), which saves the assembly pass here
     const int npt = subdomain_operator.num_points, ne = subdomain_operator.num_extended_dofs, ns = superdomain_operator.num_extended_dofs;
     memory r_sub = r.slice(0, npt), z_sub = z.slice(0, npt);
     amg::Level &L0 = amg_fem.levels[0];
     if (interface_is_identity)
     {
         // Qt_int / Q_int are identities: assemble straight into the V-cycle's right-hand side, scatter straight out of its solution
-        timer.start("subdomain.preconditioner.assemble_subdomain");
-        subdomain_operator.Qt.multiply(L0.f, r_sub);
-        timer.stop("subdomain.preconditioner.assemble_subdomain");
+        memory f_own = L0.f;
+        if (r_assembled)
+            L0.f = r_assembled->slice(0, L0.n); // the cycle reads its right-hand side in place
+        else
+        {
+            timer.start("subdomain.preconditioner.assemble_subdomain");
+            subdomain_operator.Qt.multiply(L0.f, r_sub);
+            timer.stop("subdomain.preconditioner.assemble_subdomain");
+        }
         timer.start("subdomain.preconditioner.down_leg_gpu");
         amg_fem.vcycle(num_vcycles);
         timer.stop("subdomain.preconditioner.down_leg_gpu");
+        L0.f = f_own;
         timer.start("subdomain.preconditioner.unassemble_subdomain");
         subdomain_operator.Q.multiply(z_sub, L0.u);
         timer.stop("subdomain.preconditioner.unassemble_subdomain");
         return;
     }
-    timer.start("subdomain.preconditioner.assemble_subdomain");
-    subdomain_operator.Qt.multiply(work_dev[0], r_sub);
-    timer.stop("subdomain.preconditioner.assemble_subdomain");
-    if (ns > 0) work_dev[0].slice(ne, ns).copyFrom(r.slice(npt, ns), ns * sizeof(DType));
+    if (!r_assembled)
+    {
+        timer.start("subdomain.preconditioner.assemble_subdomain");
+        subdomain_operator.Qt.multiply(work_dev[0], r_sub);
+        timer.stop("subdomain.preconditioner.assemble_subdomain");
+        if (ns > 0) work_dev[0].slice(ne, ns).copyFrom(r.slice(npt, ns), ns * sizeof(DType));
+    }
     timer.start("subdomain.preconditioner.assemble_composite");
-    Qt_int.multiply(L0.f, work_dev[0]);
+    Qt_int.multiply(L0.f, r_assembled ? *r_assembled : work_dev[0]);
     timer.stop("subdomain.preconditioner.assemble_composite");
     timer.start("subdomain.preconditioner.down_leg_gpu");
     amg_fem.vcycle(num_vcycles);
@@ -954,6 +967,17 @@ void Subdomain<DType>::assemble_weighted(const memory &dst, const memory &src)
 {
     const int npt = subdomain_operator.num_points, ne = subdomain_operator.num_extended_dofs, ns = superdomain_operator.num_extended_dofs;
     subdomain_operator.Qt.multiply_weight(dst, src.slice(0, npt), norm_weight);
+    if (ns > 0) src.slice(npt, ns).copyTo(dst.slice(ne, ns), ns * sizeof(DType));
+}
+
+// dst[0:ne] = Qt src_sub ; dst[ne:ne+ns] = src_sup: the assembled copy without the 0/1 norm weight, which the inner products
+// apply themselves (w in {0,1}, so sum w (w a)(w b) and sum w a b are the same number); it is also exactly the vector the
+// low-order preconditioner assembles from its input (tpp:3994-3999)
+template <typename DType>
+void Subdomain<DType>::assemble(const memory &dst, const memory &src)
+{
+    const int npt = subdomain_operator.num_points, ne = subdomain_operator.num_extended_dofs, ns = superdomain_operator.num_extended_dofs;
+    subdomain_operator.Qt.multiply(dst, src.slice(0, npt));
     if (ns > 0) src.slice(npt, ns).copyTo(dst.slice(ne, ns), ns * sizeof(DType));
 }
 
@@ -1005,6 +1029,10 @@ void Subdomain<DType>::gmres_body(const memory &u_l, const memory &f_l)
     dev::check_rc(prfdd_initialize_arrays(dp(u_k), dp(r_k), dp(f), nvl, st()), "initialize_arrays");
     timer.stop("subdomain.vector_operations");
 
+    // aV[i] holds the assembled copy [Qt V_i,sub | V_i,sup] of every basis vector WITHOUT the norm weight (assemble()); the
+    // weight enters the reductions.  One Arnoldi column is then: V-cycle on aV[j] directly, operator, ONE assembly of the new
+    // column, one fused multi-dot, one fused orthogonalise+norm on the assembled side, the device-side Hessenberg update, and
+    // one launch that forms V[j+1] and aV[j+1] (the reference: 2(j+1)+2 assemblies, j+3 host-synchronising reductions, j+3 axpys)
     int iter = 0;
     bool first = true;
     while (iter < max_iterations)
@@ -1015,14 +1043,14 @@ void Subdomain<DType>::gmres_body(const memory &u_l, const memory &f_l)
             math.vector_vector_addition(r_k, 1.0, f, -1.0, r_k, nvl);
         }
         timer.start("subdomain.residual_norm");
-        residual_norm_dev(r_k, red); // also leaves aq = w Qt r_k
+        assemble(aq, r_k);
+        dev::check_rc(prfdd_weighted_inner_product(ws, red, dp(aq), dp(aq), dp(norm_weight), next, st()), "Subdomain::residual_norm");
         dev::check_rc(prfdd_gmres_begin_cycle(K, first ? 1 : 0, st()), "gmres_begin_cycle");
         timer.stop("subdomain.residual_norm");
         first = false;
 
-        // V0 = r / gamma0 ; cached assembled copy aV0 = aq / gamma0
-        dev::check_rc(prfdd_vector_scaling_dev(dp(V[0]), inv_gamma0, nullptr, dp(r_k), nvl, st()), "V0");
-        dev::check_rc(prfdd_vector_scaling_dev(dp(aV[0]), inv_gamma0, nullptr, dp(aq), next, st()), "aV0");
+        // V0 = r / gamma0 and its assembled copy
+        dev::check_rc(prfdd_arnoldi_next(dp(V[0]), dp(r_k), nullptr, hcol, 0, inv_gamma0, nvl, dp(aV[0]), dp(aq), next, st()), "V0");
 
         int j;
         for (j = 0; j < num_vectors; j++)
@@ -1030,7 +1058,7 @@ void Subdomain<DType>::gmres_body(const memory &u_l, const memory &f_l)
             iter++;
             timer.start("subdomain.preconditioner");
             if (use_preconditioner)
-                low_order_preconditioner(Z[j], V[j]);
+                low_order_preconditioner(Z[j], V[j], &aV[j]);
             else
                 direct_stiffness_summation(Z[j], V[j]);
             timer.stop("subdomain.preconditioner");
@@ -1039,34 +1067,25 @@ void Subdomain<DType>::gmres_body(const memory &u_l, const memory &f_l)
             stiffness_matrix(q_k, Z[j]);
             timer.stop("subdomain.operator_application");
 
-            // Gram-Schmidt (tpp:4389-4401): H[i][j] = <w Qt q, w Qt V_i>_w for i <= j in one pass
+            // Gram-Schmidt (tpp:4389-4401): H[i][j] = <Qt q, Qt V_i>_w for i <= j in one pass
             timer.start("subdomain.inner_products");
-            assemble_weighted(aq, q_k);
-            {
-                std::vector<const double *> vp(j + 1);
-                for (int i = 0; i <= j; i++) vp[i] = dp(aV[i]);
-                dev::check_rc(prfdd_multi_inner_product(ws, hcol, dp(aq), vp.data(), dp(norm_weight), j + 1, next, st()), "multi_inner_product");
-            }
+            assemble(aq, q_k);
+            std::vector<const double *> ap(j + 1), vp(j + 1);
+            for (int i = 0; i <= j; i++) { ap[i] = dp(aV[i]); vp[i] = dp(V[i]); }
+            dev::check_rc(prfdd_multi_inner_product(ws, hcol, dp(aq), ap.data(), dp(norm_weight), j + 1, next, st()), "multi_inner_product");
             timer.stop("subdomain.inner_products");
-            timer.start("subdomain.vector_operations");
-            {
-                std::vector<const double *> vp(j + 1);
-                for (int i = 0; i <= j; i++) vp[i] = dp(V[i]);
-                dev::check_rc(prfdd_multi_axpy_dev(dp(q_k), vp.data(), hcol, 1, -1.0, j + 1, nvl, st()), "multi_axpy");
-            }
-            timer.stop("subdomain.vector_operations");
 
+            // orthogonalise the assembled copy and take its norm (tpp:4396-4412) -- Qt is linear, no second assembly
             timer.start("subdomain.residual_norm");
-            residual_norm_dev(q_k, red); // aq = w Qt q (orthogonalised)
+            dev::check_rc(prfdd_orthogonalize_norm(ws, red, dp(aq), ap.data(), hcol, dp(norm_weight), j + 1, next, st()), "orthogonalize_norm");
             dev::check_rc(prfdd_gmres_column(K, j, iter, max_iterations, tolerance, 0, st()), "gmres_column");
             timer.stop("subdomain.residual_norm");
 
             if (iter >= max_iterations) { j++; break; } // statically known: the reference breaks here too (tpp:4449-4453)
+            timer.start("subdomain.vector_operations");
             if (j + 1 < num_vectors + 1)
-            {
-                dev::check_rc(prfdd_vector_scaling_dev(dp(V[j + 1]), inv_alpha, nullptr, dp(q_k), nvl, st()), "V_j+1");
-                dev::check_rc(prfdd_vector_scaling_dev(dp(aV[j + 1]), inv_alpha, nullptr, dp(aq), next, st()), "aV_j+1");
-            }
+                dev::check_rc(prfdd_arnoldi_next(dp(V[j + 1]), dp(q_k), vp.data(), hcol, j + 1, inv_alpha, nvl, dp(aV[j + 1]), dp(aq), next, st()), "V_j+1");
+            timer.stop("subdomain.vector_operations");
         }
         dev::check_rc(prfdd_gmres_end_cycle(K, num_vectors, st()), "gmres_end_cycle");
         // Sum Arnoldi vectors (tpp:4472-4478); coefficients beyond the last used column are exactly 0 and skipped
@@ -1311,8 +1330,7 @@ int Subdomain<DType>::time_spmv(int reps, double out[6])
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     auto step = [&](amg::Level &L) {
-        return prfdd_cheby_step(L.u.as<double>(), L.t1.as<double>(), L.dA.ptr.as<int>(), L.dA.col.as<int>(), L.dA.val.as<double>(), L.t0.as<double>(), L.r.as<double>(), L.ds.as<double>(),
-                                L.coefs[0], 0, 0, L.n, L.dA.tpr, stream);
+        return prfdd_csrm_cheby_step(L.u.as<double>(), L.t1.as<double>(), &L.dA.desc, L.t0.as<double>(), L.r.as<double>(), L.ds.as<double>(), L.coefs[0], 0, 0, stream);
     };
     for (int w = 0; w < 4; w++) { step(amg_fem.levels[0]); step(amg_fem.levels[1]); }
     cudaEventRecord(e0, stream);
@@ -1331,7 +1349,7 @@ int Subdomain<DType>::time_spmv(int reps, double out[6])
     for (int l = 0; l < 2; l++)
     {
         const amg::Level &L = amg_fem.levels[l];
-        bytes += 0.5 * (12.0 * L.A.nnz() + 4.0 * (L.n + 1) + 40.0 * L.n);
+        bytes += 0.5 * (12.0 * L.A.nnz() + 4.0 * (L.n + 1) + 32.0 * L.n); // col 4 + val 8 per entry; ptr; t_in, ds, r read and t_out written once per row
         out[2 + 2 * l] = L.n;
         out[3 + 2 * l] = L.A.nnz();
     }

@@ -9,7 +9,10 @@
 // around an SpMV (scaling by ds, c*r + v, u += ds*w, f - A u) is done in the SpMV epilogue, so one
 // Chebyshev smoothing of order 2 is 2 launches and 2 passes over A instead of 7 launches.
 #include "common.cuh"
-#include <unordered_map>
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
 
 namespace prfdd
 {
@@ -85,66 +88,325 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
 
 // Long rows.  A warp finishes when its longest row does, and under load one dependent col -> x step costs microseconds, so a
 // thread that walks a 60- or 300-entry row alone (hanging-node rows of the non-conforming composite grid in the low-order
-// matrix, and the columns of its Q that become rows of Q^T) outlasts the rest of the kernel.  Matrices can register the
-// list of their rows longer than a threshold (prfdd_csr_set_long_rows): k_spmv then skips those rows and k_spmv_long gives
-// each a whole warp.  Same epilogue, fixed summation order.
-template <class Epi>
-__global__ void __launch_bounds__(kSpThreads) k_spmv_long(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, const int *__restrict__ rows, int count, Epi epi)
+// matrix, and the columns of its Q that become rows of Q^T) outlasts the rest of the kernel.  A matrix descriptor can carry the
+// list of its rows longer than a threshold (prfdd_csr_matrix::long_rows): the row-group kernels then skip those rows and
+// k_spmv_long gives each a whole warp.  Same epilogue, fixed summation order.
+template <bool UNIT, class Epi>
+__global__ void __launch_bounds__(kSpThreads) k_spmv_long(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, const int *__restrict__ rows, int count, int num_rows, Epi epi)
 {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (kSpThreads / 32) + (threadIdx.x >> 5);
     if (w >= count) return; // whole warps leave together
     const int row = rows[w];
+    if (row >= num_rows) return;
     double acc = 0.0;
-    for (int j = ptr[row] + lane; j < ptr[row + 1]; j += 32) acc += val[j] * x[col[j]];
+    for (int j = ptr[row] + lane; j < ptr[row + 1]; j += 32) acc += UNIT ? x[col[j]] : val[j] * x[col[j]];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) epi(row, acc);
 }
 
-struct LongRows
-{
-    const int *rows;
-    int count, threshold;
-};
-static std::unordered_map<const void *, LongRows> g_long_rows; // keyed by the device address of the row-pointer array
+// ---------------------------------------------------------------------------------------------
+// warp-staged SpMV
+// ---------------------------------------------------------------------------------------------
+// Why: ncu on the row-group kernel above (profiles/r1_ncu_full_spmv.txt, source page) shows the SM's L1 tag stage as the
+// bound, not DRAM: 0.87 tag requests per SM cycle on AMG levels 0 and 1, and 75 % of them are col/val loads -- lanes of a warp
+// read 4-8 short row segments that lie 28-216 bytes apart, so every trip re-touches the same 7-15 cache lines -- issued in a
+// dependent chain col -> x.  Here a warp owns a group of G consecutive rows, whose col/val entries are ONE contiguous slice of
+// the CSR arrays: the slice is copied to shared memory with 16-byte cp.async (one tag lookup per 128-byte line, L1 bypassed,
+// asynchronous: the slice of the warp's next group is in flight while the current one is consumed), and the lanes then walk
+// their rows out of shared memory, so the only L1 traffic left is the x gather, which the lanes can issue back to back
+// because the column indices are already on chip.  Per-row summation order is that of k_spmv: results are bit-identical.
+// Groups whose slice exceeds the staging capacity (clusters of hanging-node rows) take the direct path inside the same kernel.
+constexpr int kStWarps = kSpThreads / 32;
 
-template <int TPR, class Epi>
-static void launch_spmv(const int *ptr, const int *col, const double *val, const double *x, int row_start, int num_rows, const LongRows *lr, cudaStream_t st, Epi epi)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, int src_bytes)
 {
-    // two rows per sub-warp once the matrix is large enough to fill the machine with half as many warps
-    // (AMG level 1 of the 16^3 N=7 problem, 27 entries/row: 54.9 -> 49.1 us; profiles/r1_notes.txt)
-    const bool two = TPR >= 4 && (long long)num_rows * TPR >= (1ll << 21);
-    const int grid = stream_grid((long long)num_rows * TPR / (two ? 2 : 1), kSpThreads, 1, 16);
-    const int skip_len = lr ? lr->threshold : 0x7fffffff;
-    if (two) k_spmv<TPR, 2><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, skip_len, epi);
-    else k_spmv<TPR, 1><<<grid, kSpThreads, 0, st>>>(ptr, col, val, x, row_start, num_rows, skip_len, epi);
-    if (lr) k_spmv_long<<<(lr->count + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(ptr, col, val, x, lr->rows, lr->count, epi);
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// the rows of one group, RPG at a time: row (g * RPW + sub) of the group in pass g; cs / vs are indexed by the CSR position
+// minus `base` (shared-memory stage) or by the CSR position itself (direct path, base = 0)
+template <int TPR, int RPG, bool UNIT, class Epi>
+__device__ __forceinline__ void group_rows(const int *cs, const double *vs, int base, const double *__restrict__ x, int p, int pend, long long r0, int num_rows, int skip_len, Epi &epi)
+{
+    constexpr int RPW = 32 / TPR;
+    constexpr int G = RPW * RPG;
+    constexpr int U = TPR == 1 ? 4 : 2; // entries per row and trip in flight
+    const int lane = threadIdx.x % TPR;
+    const int sub = (threadIdx.x & 31) / TPR;
+    int j[RPG], e[RPG];
+    bool skip[RPG];
+    double acc[RPG];
+#pragma unroll
+    for (int g = 0; g < RPG; g++)
+    {
+        const int rg = g * RPW + sub; // row of the group
+        const int s = __shfl_sync(0xffffffffu, p, rg);
+        const int en = __shfl_sync(0xffffffffu, p, (rg + 1) & 31);
+        e[g] = (rg + 1 >= 32) ? pend : en; // lane G of a group with G < 32 rows holds pend itself
+        skip[g] = e[g] - s > skip_len;
+        if (skip[g] || r0 + rg >= num_rows) e[g] = s;
+        j[g] = s + lane - base;
+        e[g] -= base;
+        acc[g] = 0.0;
+    }
+    bool more = false;
+#pragma unroll
+    for (int g = 0; g < RPG; g++) more |= j[g] < e[g];
+    while (more)
+    {
+        int c[RPG][U];
+        double v[RPG][U];
+#pragma unroll
+        for (int g = 0; g < RPG; g++)
+#pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+                const int k = j[g] + u * TPR;
+                const bool on = k < e[g];
+                c[g][u] = on ? cs[k] : -1;
+                v[g][u] = (on && !UNIT) ? vs[k] : 0.0;
+            }
+        double xv[RPG][U];
+#pragma unroll
+        for (int g = 0; g < RPG; g++)
+#pragma unroll
+            for (int u = 0; u < U; u++) xv[g][u] = c[g][u] >= 0 ? x[c[g][u]] : 0.0;
+        more = false;
+#pragma unroll
+        for (int g = 0; g < RPG; g++)
+        {
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (c[g][u] >= 0) acc[g] += UNIT ? xv[g][u] : v[g][u] * xv[g][u];
+            j[g] += U * TPR;
+            more |= j[g] < e[g];
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < RPG; g++)
+    {
+#pragma unroll
+        for (int o = TPR / 2; o > 0; o >>= 1) acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], o, TPR);
+        const long long r = r0 + g * RPW + sub;
+        if (r < num_rows && lane == 0 && !skip[g]) epi((int)r, acc[g]);
+    }
 }
 
+template <int TPR, int RPG, bool UNIT, class Epi>
+__global__ void __launch_bounds__(kSpThreads) k_spmv_staged(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, int num_rows, int num_nnz, int cap, int skip_len, Epi epi)
+{
+    constexpr int G = (32 / TPR) * RPG;
+    extern __shared__ __align__(16) unsigned char stage_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    // per warp: two buffers of [cap doubles | cap ints] (UNIT: ints only)
+    const size_t buf_bytes = (size_t)cap * (UNIT ? 4 : 12);
+    unsigned char *mine = stage_smem + (size_t)warp * 2 * buf_bytes;
+    const long long num_groups = ((long long)num_rows + G - 1) / G;
+    const long long stride = (long long)gridDim.x * kStWarps;
+    long long g0 = (long long)blockIdx.x * kStWarps + warp;
+    if (g0 >= num_groups) return; // whole warps leave together
+
+    auto load_ptrs = [&](long long g, int &p, int &pend) {
+        const long long r = g * G + lane;
+        p = ptr[r < num_rows ? r : num_rows];
+        if (G < 32) pend = __shfl_sync(0xffffffffu, p, G);
+        else pend = ptr[(g + 1) * G < num_rows ? (g + 1) * G : num_rows];
+    };
+    // copies the slice [base, pend) of col / val into buffer b; nothing is issued for an oversized slice
+    auto issue = [&](int b, int p, int pend) {
+        const int base = __shfl_sync(0xffffffffu, p, 0) & ~3;
+        const int count = pend - base;
+        if (count <= cap)
+        {
+            unsigned char *dst = mine + (size_t)b * buf_bytes;
+            int *cdst = reinterpret_cast<int *>(dst + (UNIT ? 0 : (size_t)cap * 8));
+            for (int k = 4 * lane; k < count; k += 128)
+            {
+                const int left = num_nnz - (base + k);
+                cp_async16(cdst + k, col + base + k, left >= 4 ? 16 : left * 4);
+            }
+            if (!UNIT)
+            {
+                double *vdst = reinterpret_cast<double *>(dst);
+                for (int k = 2 * lane; k < count; k += 64)
+                {
+                    const int left = num_nnz - (base + k);
+                    cp_async16(vdst + k, val + base + k, left >= 2 ? 16 : left * 8);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    int p_cur, pend_cur, p_nxt = 0, pend_nxt = 0;
+    load_ptrs(g0, p_cur, pend_cur);
+    long long g1 = g0 + stride;
+    if (g1 < num_groups) load_ptrs(g1, p_nxt, pend_nxt);
+    int b = 0;
+    issue(b, p_cur, pend_cur);
+    while (true)
+    {
+        const long long g2 = g1 + stride;
+        int p_n2 = 0, pend_n2 = 0;
+        if (g2 < num_groups) load_ptrs(g2, p_n2, pend_n2); // consumed one trip later
+        if (g1 < num_groups) issue(b ^ 1, p_nxt, pend_nxt);
+        else cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const int base = __shfl_sync(0xffffffffu, p_cur, 0) & ~3;
+        if (pend_cur - base <= cap)
+        {
+            const unsigned char *src = mine + (size_t)b * buf_bytes;
+            group_rows<TPR, RPG, UNIT>(reinterpret_cast<const int *>(src + (UNIT ? 0 : (size_t)cap * 8)), reinterpret_cast<const double *>(src), base, x, p_cur, pend_cur, g0 * G, num_rows, skip_len, epi);
+        }
+        else
+            group_rows<TPR, RPG, UNIT>(col, val, 0, x, p_cur, pend_cur, g0 * G, num_rows, skip_len, epi);
+        __syncwarp();
+        if (g1 >= num_groups) break;
+        g0 = g1; g1 = g2;
+        p_cur = p_nxt; pend_cur = pend_nxt;
+        p_nxt = p_n2; pend_nxt = pend_n2;
+        b ^= 1;
+    }
+}
+
+// one entry per row (ptr == NULL): out = epi(row, [val] x[col[row]])  -- Q of a conforming region
+template <bool UNIT, class Epi>
+__global__ void __launch_bounds__(256) k_spmv_single(const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, int row_start, int num_rows, Epi epi)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = row_start + (long long)blockIdx.x * blockDim.x + threadIdx.x; r < row_start + num_rows; r += stride) epi((int)r, UNIT ? x[col[r]] : val[r] * x[col[r]]);
+}
+
+static int g_spmv_variant = -1; // -1: read PRFDD_SPMV_VARIANT on first use; 0: row-group kernels only; 1: staged where the descriptor allows
+static int g_spmv_ctas = 0;     // CTAs per SM of the staged kernel (0: from shared memory)
+static int spmv_variant()
+{
+    if (g_spmv_variant < 0)
+    {
+        const char *e = getenv("PRFDD_SPMV_VARIANT");
+        g_spmv_variant = e ? atoi(e) : 1;
+        const char *c = getenv("PRFDD_SPMV_CTAS");
+        g_spmv_ctas = c ? atoi(c) : 0;
+    }
+    return g_spmv_variant;
+}
+
+template <int TPR, int RPG, bool UNIT, class Epi>
+static void launch_staged(const prfdd_csr_matrix &A, const double *x, cudaStream_t st, Epi epi)
+{
+    constexpr int G = (32 / TPR) * RPG;
+    const size_t smem = (size_t)kStWarps * 2 * A.stage_cap * (UNIT ? 4 : 12);
+    static size_t smem_set = 0; // per instantiation
+    if (smem > smem_set)
+    {
+        cudaFuncSetAttribute(k_spmv_staged<TPR, RPG, UNIT, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smem_set = smem;
+    }
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : per_sm > 6 ? 6 : per_sm;
+    if (g_spmv_ctas > 0 && g_spmv_ctas < per_sm) per_sm = g_spmv_ctas;
+    const long long groups = ((long long)A.num_rows + G - 1) / G;
+    long long grid = (groups + kStWarps - 1) / kStWarps;
+    const long long cap = (long long)num_sms() * per_sm;
+    if (grid > cap) grid = cap;
+    const int skip_len = A.num_long_rows > 0 ? A.long_row_threshold : 0x7fffffff;
+    k_spmv_staged<TPR, RPG, UNIT><<<(int)grid, kSpThreads, smem, st>>>(A.ptr, A.col, A.val, x, A.num_rows, A.num_nnz, A.stage_cap, skip_len, epi);
+}
+
+template <int TPR, bool UNIT, class Epi>
+static void launch_spmv(const prfdd_csr_matrix &A, const double *x, int row_start, int num_rows, cudaStream_t st, Epi epi)
+{
+    const bool lr = x && row_start == 0 && TPR < 32 && A.num_long_rows > 0 && A.long_rows;
+    if constexpr (!UNIT)
+    {
+        // two rows per sub-warp once the matrix is large enough to fill the machine with half as many warps
+        // (AMG level 1 of the 16^3 N=7 problem, 27 entries/row: 54.9 -> 49.1 us; profiles/r1_notes.txt)
+        const bool two = TPR >= 4 && (long long)num_rows * TPR >= (1ll << 21);
+        const int grid = stream_grid((long long)num_rows * TPR / (two ? 2 : 1), kSpThreads, 1, 16);
+        const int skip_len = lr ? A.long_row_threshold : 0x7fffffff;
+        if (two) k_spmv<TPR, 2><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
+        else k_spmv<TPR, 1><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
+    }
+    if (lr) k_spmv_long<UNIT><<<(A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
+}
+
+// dispatch on the descriptor.  `heavy`: epilogues of the V-cycle get every staged shape; the others a reduced set
 template <class Epi>
-static int spmv(const int *ptr, const int *col, const double *val, const double *x, int row_start, int num_rows, int tpr, cudaStream_t st, Epi epi)
+static int spmv(const prfdd_csr_matrix &A, const double *x, int row_start, int num_rows, cudaStream_t st, Epi epi)
 {
     if (num_rows <= 0) return 0;
-    if (tpr <= 0) tpr = 4;
-    const LongRows *lr = nullptr;
-    if (x && row_start == 0 && tpr < 32 && !g_long_rows.empty())
+    if (!A.col) return -8;
+    const bool unit = A.val == nullptr;
+    if (!A.ptr)
     {
-        auto it = g_long_rows.find(ptr);
-        if (it != g_long_rows.end()) lr = &it->second;
+        // one entry per row
+        if (!x) return -8;
+        if (unit) k_spmv_single<true><<<stream_grid(num_rows, 256, 2, 8), 256, 0, st>>>(A.col, nullptr, x, row_start, num_rows, epi);
+        else k_spmv_single<false><<<stream_grid(num_rows, 256, 2, 8), 256, 0, st>>>(A.col, A.val, x, row_start, num_rows, epi);
+        return launched();
+    }
+    int tpr = A.threads_per_row > 0 ? A.threads_per_row : 4;
+    const bool lr = x && row_start == 0 && tpr < 32 && A.num_long_rows > 0 && A.long_rows;
+    const bool staged = x && row_start == 0 && num_rows == A.num_rows && A.stage_cap > 0 && A.num_nnz > 0 && (spmv_variant() == 1 || unit);
+    if (unit && !staged) return -9; // a matrix without values needs a staging plan (prfdd_csr_plan)
+    if (staged)
+    {
+        const int rpg = A.stage_rows_per_lane_group;
+        bool done = true;
+#define PRFDD_STAGED(T, R)                                                   \
+    if (unit) launch_staged<T, R, true>(A, x, st, epi);                      \
+    else launch_staged<T, R, false>(A, x, st, epi);
+        if (tpr == 1) { PRFDD_STAGED(1, 1) }
+        else if (tpr == 2) { PRFDD_STAGED(2, 1) }
+        else if (tpr == 4 && rpg == 2) { PRFDD_STAGED(4, 2) }
+        else if (tpr == 4) { PRFDD_STAGED(4, 1) }
+        else if (tpr == 8 && rpg == 2) { PRFDD_STAGED(8, 2) }
+        else if (tpr == 8) { PRFDD_STAGED(8, 1) }
+        else if (tpr == 16) { PRFDD_STAGED(16, 1) }
+        else done = false;
+#undef PRFDD_STAGED
+        if (done)
+        {
+            if (lr)
+            {
+                if (unit) k_spmv_long<true><<<(A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
+                else k_spmv_long<false><<<(A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
+                prfdd_launch_count_add(1);
+            }
+            return launched();
+        }
+        if (unit) return -9;
     }
     switch (tpr)
     {
-    case 1: launch_spmv<1>(ptr, col, val, x, row_start, num_rows, lr, st, epi); break;
-    case 2: launch_spmv<2>(ptr, col, val, x, row_start, num_rows, lr, st, epi); break;
-    case 4: launch_spmv<4>(ptr, col, val, x, row_start, num_rows, lr, st, epi); break;
-    case 8: launch_spmv<8>(ptr, col, val, x, row_start, num_rows, lr, st, epi); break;
-    case 16: launch_spmv<16>(ptr, col, val, x, row_start, num_rows, lr, st, epi); break;
-    case 32: launch_spmv<32>(ptr, col, val, x, row_start, num_rows, lr, st, epi); break;
+    case 1: launch_spmv<1, false>(A, x, row_start, num_rows, st, epi); break;
+    case 2: launch_spmv<2, false>(A, x, row_start, num_rows, st, epi); break;
+    case 4: launch_spmv<4, false>(A, x, row_start, num_rows, st, epi); break;
+    case 8: launch_spmv<8, false>(A, x, row_start, num_rows, st, epi); break;
+    case 16: launch_spmv<16, false>(A, x, row_start, num_rows, st, epi); break;
+    case 32: launch_spmv<32, false>(A, x, row_start, num_rows, st, epi); break;
     default: return -6;
     }
     if (lr) prfdd_launch_count_add(1);
     return launched();
+}
+
+// the pointer-argument entry points (the reference's kernel signatures + one lanes-per-row hint): no long-row list, no staging
+static prfdd_csr_matrix plain(const int *ptr, const int *col, const double *val, int num_rows, int tpr)
+{
+    prfdd_csr_matrix A = {};
+    A.ptr = ptr; A.col = col; A.val = val;
+    A.num_rows = num_rows; A.num_nnz = -1;
+    A.threads_per_row = tpr <= 0 ? 4 : tpr;
+    return A;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -245,46 +507,115 @@ int prfdd_scatter_assign(double *dst, const double *buf, const int *idx, int cou
     return launched();
 }
 
-int prfdd_csr_set_long_rows(const int *ptr, const int *rows, int count, int threshold)
+// lanes per row from the average row length (measured on B200, profiles/r1_spmv_tpr.txt and r1_notes.txt)
+static int lanes_per_row(double avg, int num_rows) { return avg <= 10 ? 1 : avg <= 18 ? 2 : (avg > 60 && num_rows < 50000) ? 16 : 8; }
+
+int prfdd_csr_plan(prfdd_csr_matrix *A, const int *ptr_host, int *long_rows_host, int capacity)
 {
-    if (!ptr) return -8;
-    if (!rows || count <= 0) g_long_rows.erase(ptr);
-    else g_long_rows[ptr] = LongRows{rows, count, threshold};
+    if (!A || !ptr_host || A->num_rows < 0) return -8;
+    static const bool no_long = getenv("PRFDD_SPMV_NO_LONG_ROWS") != nullptr;
+    const int n = A->num_rows;
+    const int nnz = ptr_host[n];
+    A->num_nnz = nnz;
+    A->long_rows = nullptr;
+    A->num_long_rows = 0;
+    A->long_row_threshold = 0;
+    A->stage_cap = 0;
+    A->stage_rows_per_lane_group = 1;
+    const double avg = (double)nnz / (n > 0 ? n : 1);
+    const int tpr = lanes_per_row(avg, n);
+    A->threads_per_row = tpr;
+    if (n == 0 || nnz == 0) return 0;
+    // rows much longer than the average (and than the lanes that walk them can absorb) go to the warp-per-row launch; worth a
+    // second launch only when some row is several times the threshold (the tail it removes is then longer than the launch)
+    const int threshold = std::max(std::max(16, 4 * tpr), (int)std::ceil(3.0 * avg));
+    int count = 0, longest = 0;
+    for (int r = 0; r < n; r++)
+    {
+        const int len = ptr_host[r + 1] - ptr_host[r];
+        longest = std::max(longest, len);
+        if (len > threshold) count++;
+    }
+    int listed = 0;
+    if (!no_long && count > 0 && tpr < 32 && longest >= 4 * threshold && (double)count <= 0.05 * n)
+    {
+        if (count > capacity || !long_rows_host) return -count;
+        for (int r = 0; r < n; r++)
+            if (ptr_host[r + 1] - ptr_host[r] > threshold) long_rows_host[listed++] = r;
+        A->long_row_threshold = threshold;
+    }
+    // staging plan: G consecutive rows per warp and trip; the capacity covers (nearly) every group
+    const int rpg = (tpr >= 4 && tpr < 16 && avg <= 40.0) ? 2 : 1;
+    if (tpr <= 16)
+    {
+        const int G = (32 / tpr) * rpg;
+        const long long groups = ((long long)n + G - 1) / G;
+        std::vector<int> cnt((size_t)groups);
+        for (long long g = 0; g < groups; g++)
+        {
+            const long long r0 = g * G, r1 = std::min<long long>(r0 + G, n);
+            cnt[(size_t)g] = ptr_host[r1] - (ptr_host[r0] & ~3);
+        }
+        std::vector<int> sorted(cnt);
+        const size_t k = (size_t)std::min<long long>(groups - 1, (long long)std::ceil(0.995 * groups));
+        std::nth_element(sorted.begin(), sorted.begin() + k, sorted.end());
+        const int p995 = sorted[k];
+        const int mx = *std::max_element(cnt.begin(), cnt.end());
+        constexpr int kCapMax = 544; // 2 CTAs of 8 warps per SM: 8 * 2 * 544 * 12 B = 102 KB each
+        int cap = (mx <= kCapMax || mx <= p995 + p995 / 4) ? mx : p995;
+        cap = ((std::max(cap, 32) + 31) / 32) * 32;
+        if (cap <= kCapMax)
+        {
+            A->stage_cap = cap;
+            A->stage_rows_per_lane_group = rpg;
+        }
+    }
+    return listed;
+}
+
+int prfdd_csr_set_spmv_variant(int variant, int ctas_per_sm)
+{
+    spmv_variant();
+    g_spmv_variant = variant ? 1 : 0;
+    g_spmv_ctas = ctas_per_sm;
     return 0;
 }
 
-int prfdd_csr_multiply(double *Au, const int *ptr, const int *col, const double *val, const double *u, int num_rows, int tpr, prfdd_stream_t stream)
+// ---- descriptor entry points ----------------------------------------------------------------
+int prfdd_csrm_multiply(double *Au, const prfdd_csr_matrix *A, const double *u, prfdd_stream_t stream)
 {
-    return spmv(ptr, col, val, u, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) { Au[row] = ax; });
+    return spmv(*A, u, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) { Au[row] = ax; });
 }
 
-int prfdd_csr_multiply_range(double *Au, const int *ptr, const int *col, const double *val, const double *u, int row_start, int row_end, int tpr, prfdd_stream_t stream)
+int prfdd_csrm_multiply_range(double *Au, const prfdd_csr_matrix *A, const double *u, int row_start, int row_end, prfdd_stream_t stream)
 {
     if (row_end < row_start) return -7; // csr_matrix.tpp:319-323
-    return spmv(ptr, col, val, u, row_start, row_end - row_start + 1, tpr, S(stream), [=] __device__(int row, double ax) { Au[row] = ax; });
+    return spmv(*A, u, row_start, row_end - row_start + 1, S(stream), [=] __device__(int row, double ax) { Au[row] = ax; });
 }
 
-int prfdd_csr_multiply_weight(double *Au, const int *ptr, const int *col, const double *val, const double *u, const double *weight, int num_rows, int tpr, prfdd_stream_t stream)
+int prfdd_csrm_multiply_weight(double *Au, const prfdd_csr_matrix *A, const double *u, const double *weight, prfdd_stream_t stream)
 {
-    return spmv(ptr, col, val, u, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) { Au[row] = ax * weight[row]; });
+    return spmv(*A, u, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) { Au[row] = ax * weight[row]; });
 }
 
-int prfdd_csr_matvec(double *y, const int *ptr, const int *col, const double *val, const double *x, double alpha, double beta, int num_rows, int tpr, prfdd_stream_t stream)
+int prfdd_csrm_matvec(double *y, const prfdd_csr_matrix *A, const double *x, double alpha, double beta, prfdd_stream_t stream)
 {
     if (beta == 0.0)
-        return spmv(ptr, col, val, x, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) { y[row] = alpha * ax; });
-    return spmv(ptr, col, val, x, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) { y[row] = alpha * ax + beta * y[row]; });
+        return spmv(*A, x, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) { y[row] = alpha * ax; });
+    return spmv(*A, x, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) { y[row] = alpha * ax + beta * y[row]; });
 }
 
-int prfdd_csr_residual(double *v, const int *ptr, const int *col, const double *val, const double *u, const double *f, int num_rows, int tpr, prfdd_stream_t stream)
+int prfdd_csrm_residual(double *v, const prfdd_csr_matrix *A, const double *u, const double *f, prfdd_stream_t stream)
 {
-    return spmv(ptr, col, val, u, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) { v[row] = f[row] - ax; });
+    return spmv(*A, u, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) { v[row] = f[row] - ax; });
 }
 
-int prfdd_cheby_residual(double *r, double *t, const int *ptr, const int *col, const double *val, const double *u, const double *f, const double *ds, double c_hi, int num_rows, int tpr, prfdd_stream_t stream)
+int prfdd_csrm_cheby_residual(double *r, double *t, const prfdd_csr_matrix *A, const double *u, const double *f, const double *ds, double c_hi, prfdd_stream_t stream)
 {
-    // u == NULL: u = 0, the product A u is skipped (x == nullptr in k_spmv) and TPR is irrelevant
-    return spmv(ptr, col, val, u, 0, num_rows, u ? tpr : 1, S(stream), [=] __device__(int row, double ax) {
+    // u == NULL: u = 0, the product A u is skipped (x == nullptr in k_spmv) and the launch shape is irrelevant
+    prfdd_csr_matrix B = *A;
+    if (!u) B.threads_per_row = 1;
+    return spmv(B, u, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) {
         const double d = ds[row];
         const double rr = d * (f[row] - ax);
         r[row] = rr;
@@ -292,10 +623,10 @@ int prfdd_cheby_residual(double *r, double *t, const int *ptr, const int *col, c
     });
 }
 
-int prfdd_restrict_cheby_residual(double *f, double *r, double *t, const int *ptr, const int *col, const double *val, const double *v, const double *ds, double c_hi, int num_rows, int tpr, prfdd_stream_t stream)
+int prfdd_csrm_restrict_cheby_residual(double *f, double *r, double *t, const prfdd_csr_matrix *R, const double *v, const double *ds, double c_hi, prfdd_stream_t stream)
 {
     // f = R v fused with the zero-guess head of the coarse level's smoothing: r = ds f, t = ds (c_hi r)
-    return spmv(ptr, col, val, v, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) {
+    return spmv(*R, v, 0, R->num_rows, S(stream), [=] __device__(int row, double ax) {
         const double d = ds[row];
         const double rr = d * ax;
         f[row] = ax;
@@ -304,24 +635,73 @@ int prfdd_restrict_cheby_residual(double *f, double *r, double *t, const int *pt
     });
 }
 
-int prfdd_cheby_step(double *u, double *t_out, const int *ptr, const int *col, const double *val, const double *t_in, const double *r, const double *ds, double c, int last, int u_is_zero, int num_rows, int tpr, prfdd_stream_t stream)
+int prfdd_csrm_cheby_step(double *u, double *t_out, const prfdd_csr_matrix *A, const double *t_in, const double *r, const double *ds, double c, int last, int u_is_zero, prfdd_stream_t stream)
 {
     if (last)
     {
         if (u_is_zero)
-            return spmv(ptr, col, val, t_in, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) {
+            return spmv(*A, t_in, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) {
                 const double d = ds[row];
                 u[row] = d * (c * r[row] + d * ax);
             });
-        return spmv(ptr, col, val, t_in, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) {
+        return spmv(*A, t_in, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) {
             const double d = ds[row];
             u[row] += d * (c * r[row] + d * ax);
         });
     }
-    return spmv(ptr, col, val, t_in, 0, num_rows, tpr, S(stream), [=] __device__(int row, double ax) {
+    return spmv(*A, t_in, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) {
         const double d = ds[row];
         t_out[row] = d * (c * r[row] + d * ax);
     });
+}
+
+// ---- pointer entry points: the reference's kernel arguments + one lanes-per-row hint ------------
+int prfdd_csr_multiply(double *Au, const int *ptr, const int *col, const double *val, const double *u, int num_rows, int tpr, prfdd_stream_t stream)
+{
+    const prfdd_csr_matrix A = plain(ptr, col, val, num_rows, tpr);
+    return prfdd_csrm_multiply(Au, &A, u, stream);
+}
+
+int prfdd_csr_multiply_range(double *Au, const int *ptr, const int *col, const double *val, const double *u, int row_start, int row_end, int tpr, prfdd_stream_t stream)
+{
+    const prfdd_csr_matrix A = plain(ptr, col, val, row_end + 1, tpr);
+    return prfdd_csrm_multiply_range(Au, &A, u, row_start, row_end, stream);
+}
+
+int prfdd_csr_multiply_weight(double *Au, const int *ptr, const int *col, const double *val, const double *u, const double *weight, int num_rows, int tpr, prfdd_stream_t stream)
+{
+    const prfdd_csr_matrix A = plain(ptr, col, val, num_rows, tpr);
+    return prfdd_csrm_multiply_weight(Au, &A, u, weight, stream);
+}
+
+int prfdd_csr_matvec(double *y, const int *ptr, const int *col, const double *val, const double *x, double alpha, double beta, int num_rows, int tpr, prfdd_stream_t stream)
+{
+    const prfdd_csr_matrix A = plain(ptr, col, val, num_rows, tpr);
+    return prfdd_csrm_matvec(y, &A, x, alpha, beta, stream);
+}
+
+int prfdd_csr_residual(double *v, const int *ptr, const int *col, const double *val, const double *u, const double *f, int num_rows, int tpr, prfdd_stream_t stream)
+{
+    const prfdd_csr_matrix A = plain(ptr, col, val, num_rows, tpr);
+    return prfdd_csrm_residual(v, &A, u, f, stream);
+}
+
+int prfdd_cheby_residual(double *r, double *t, const int *ptr, const int *col, const double *val, const double *u, const double *f, const double *ds, double c_hi, int num_rows, int tpr, prfdd_stream_t stream)
+{
+    const prfdd_csr_matrix A = plain(ptr, col, val, num_rows, tpr);
+    return prfdd_csrm_cheby_residual(r, t, &A, u, f, ds, c_hi, stream);
+}
+
+int prfdd_restrict_cheby_residual(double *f, double *r, double *t, const int *ptr, const int *col, const double *val, const double *v, const double *ds, double c_hi, int num_rows, int tpr, prfdd_stream_t stream)
+{
+    const prfdd_csr_matrix A = plain(ptr, col, val, num_rows, tpr);
+    return prfdd_csrm_restrict_cheby_residual(f, r, t, &A, v, ds, c_hi, stream);
+}
+
+int prfdd_cheby_step(double *u, double *t_out, const int *ptr, const int *col, const double *val, const double *t_in, const double *r, const double *ds, double c, int last, int u_is_zero, int num_rows, int tpr, prfdd_stream_t stream)
+{
+    const prfdd_csr_matrix A = plain(ptr, col, val, num_rows, tpr);
+    return prfdd_csrm_cheby_step(u, t_out, &A, t_in, r, ds, c, last, u_is_zero, stream);
 }
 
 int prfdd_dense_solve(double *x, const double *Ainv, const double *b, int n, prfdd_stream_t stream)

@@ -362,6 +362,52 @@ int prfdd_multi_inner_product(prfdd_reduce_ws *ws, double *out, const double *u,
     return rc;
 }
 
+// Arnoldi step, assembled side (subdomain.tpp:4396-4412 on the assembled copies): aq <- aq - sum_k coef[k] aV_k, same chain
+// as prfdd_multi_axpy_dev, and out[0] = sum_i w[i] aq[i]^2 of the result -- the orthogonalised column's norm without assembling
+// it again (Q^T is linear, and aV_k = Q^T V_k are kept from the previous steps)
+int prfdd_orthogonalize_norm(prfdd_reduce_ws *ws, double *out, double *aq, const double *const *aV, const double *coef, const double *w, int count, int n, prfdd_stream_t stream)
+{
+    if (count > 32) return -3;
+    PtrPack pk;
+    for (int i = 0; i < count; i++) pk.p[i] = aV[i];
+    return reduce<1>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) {
+        double acc = aq[i];
+        for (int k = 0; k < count; k++)
+        {
+            const double c = -coef[k];
+            if (c != 0.0) acc = acc + c * pk.p[k][i];
+        }
+        aq[i] = acc;
+        a[0] += acc * acc * w[i];
+    });
+}
+
+// next Arnoldi vector and its assembled copy in one launch:
+//   V_next[i] = scale * (q[i] - sum_k coef[k] V_k[i])   i < n            (vector_vector_addition chain + vector_scaling,
+//   aV_next[i] = scale * aq[i]                           i < n_assembled   subdomain.tpp:4396-4401, 4455-4458)
+// scale read from device memory; count = 0 gives the plain scaling of the cycle's first vector (tpp:4349-4352)
+int prfdd_arnoldi_next(double *V_next, const double *q, const double *const *V, const double *coef, int count, const double *scale, int n, double *aV_next, const double *aq, int n_assembled, prfdd_stream_t stream)
+{
+    if (count > 32) return -3;
+    PtrPack pk;
+    for (int i = 0; i < count; i++) pk.p[i] = V[i];
+    return map((long long)n + n_assembled, S(stream), [=] __device__(long long i) {
+        const double a = *scale;
+        if (i < n)
+        {
+            double acc = q[i];
+            for (int k = 0; k < count; k++)
+            {
+                const double c = -coef[k];
+                if (c != 0.0) acc = acc + c * pk.p[k][i];
+            }
+            V_next[i] = a * acc;
+        }
+        else
+            aV_next[i - n] = a * aq[i - n];
+    });
+}
+
 int prfdd_weighted_projection_inner_products(prfdd_reduce_ws *ws, double *out, const double *z_k, const double *r_k, const double *p_k, const double *q_k, const double *weight, int n, prfdd_stream_t stream)
 {
     return reduce<2>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[2]) {
