@@ -113,11 +113,7 @@ int prfdd_scatter_assign(double *dst, const double *buf, const int *idx, int cou
  *                 never read;
  *   ptr == NULL   exactly one entry per row, row i holds entry i (Q of a conforming region): index-map kernel;
  *   long_rows     device list of the rows longer than long_row_threshold entries: the row kernels skip them and a second
- *                 launch gives each a whole warp (hanging-node rows of the composite grid); optional;
- *   stage_cap     > 0: the warp-staged kernel may be used -- a warp copies the contiguous col/val slice of
- *                 (32 / threads_per_row) * stage_rows_per_lane_group consecutive rows to shared memory with cp.async
- *                 (double-buffered) and walks the rows from there; stage_cap = entries per buffer (multiple of 32),
- *                 groups with a longer slice read global memory directly.
+ *                 launch gives each a whole warp (hanging-node rows of the composite grid); optional.
  * prfdd_csr_plan fills the plan from the HOST copy of ptr.  A descriptor is plain data: copy it freely, keep the device
  * arrays alive while it is in use. */
 typedef struct prfdd_csr_matrix
@@ -131,17 +127,12 @@ typedef struct prfdd_csr_matrix
     const int *long_rows;
     int num_long_rows;
     int long_row_threshold;
-    int stage_rows_per_lane_group;
-    int stage_cap;
 } prfdd_csr_matrix;
-/* host-side planning: sets threads_per_row, stage_rows_per_lane_group, stage_cap and long_row_threshold of *A from
+/* host-side planning: sets threads_per_row and long_row_threshold of *A from
  * ptr_host[0..num_rows] (A->num_rows must be set; A->num_nnz is set to ptr_host[num_rows]).  The rows longer than the
  * threshold are written to long_rows_host (capacity entries) and their count is returned (0: no list needed; the caller
  * uploads the list and sets A->long_rows / A->num_long_rows).  Returns -(count) if the capacity is too small. */
 int prfdd_csr_plan(prfdd_csr_matrix *A, const int *ptr_host, int *long_rows_host, int capacity);
-/* 0: row-group kernels only, 1: warp-staged kernels where the descriptor carries a plan (default; env PRFDD_SPMV_VARIANT);
- * ctas_per_sm > 0 caps the residency of the staged kernel (measurement aid) */
-int prfdd_csr_set_spmv_variant(int variant, int ctas_per_sm);
 /* descriptor forms of the entry points below (same arithmetic, same epilogues) */
 int prfdd_csrm_multiply(double *Au, const prfdd_csr_matrix *A, const double *u, prfdd_stream_t stream);
 int prfdd_csrm_multiply_range(double *Au, const prfdd_csr_matrix *A, const double *u, int row_start, int row_end, prfdd_stream_t stream);

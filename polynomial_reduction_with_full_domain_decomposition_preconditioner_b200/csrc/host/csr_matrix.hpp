@@ -160,7 +160,7 @@ class CSR_Matrix
         long_rows = plan_csr(desc, ptr_hst.data());
         threads_per_row = desc.threads_per_row;
         static const bool no_unit = getenv("PRFDD_CSR_NO_UNIT") != nullptr;
-        unit_values = !no_unit && typeid(DType) == typeid(double) && desc.stage_cap > 0;
+        unit_values = !no_unit && typeid(DType) == typeid(double);
         for (int j = 0; j < num_nnz && unit_values; j++) unit_values = (val_hst[j] == (DType)1);
         one_entry_per_row = unit_values && num_nnz == num_rows;
         for (int i = 0; i <= num_rows && one_entry_per_row; i++) one_entry_per_row = (ptr_hst[i] == i);

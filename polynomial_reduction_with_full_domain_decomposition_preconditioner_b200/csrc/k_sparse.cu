@@ -23,7 +23,7 @@ constexpr int kSpThreads = 256;
 // shuffles are always executed by the whole warp.  RPG > 1: every sub-warp walks RPG rows at once
 // (rows r, r + 32/TPR, ...), which multiplies the independent col/val -> x load chains a lane has in
 // flight; the long rows of the coarse AMG levels are latency bound without it.
-template <int TPR, int RPG, class Epi>
+template <int TPR, int RPG, bool UNIT, class Epi>
 __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, int row_start, int num_rows, int skip_len, Epi epi)
 {
     constexpr int RPW = 32 / TPR; // rows per warp and pass
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
         }
         if constexpr (RPG == 1)
         {
-            for (int k = j[0]; k < e[0]; k += TPR) acc[0] += val[k] * x[col[k]];
+            for (int k = j[0]; k < e[0]; k += TPR) acc[0] += UNIT ? x[col[k]] : val[k] * x[col[k]];
         }
         else
         {
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
                 {
                     const bool on = j[g] < e[g];
                     c[g] = on ? col[j[g]] : 0;
-                    v[g] = on ? val[j[g]] : 0.0;
+                    v[g] = (on && !UNIT) ? val[j[g]] : 1.0;
                 }
                 more = false;
 #pragma unroll
@@ -106,177 +106,6 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv_long(const int *__restrict_
     if (lane == 0) epi(row, acc);
 }
 
-// ---------------------------------------------------------------------------------------------
-// warp-staged SpMV
-// ---------------------------------------------------------------------------------------------
-// Why: ncu on the row-group kernel above (profiles/r1_ncu_full_spmv.txt, source page) shows the SM's L1 tag stage as the
-// bound, not DRAM: 0.87 tag requests per SM cycle on AMG levels 0 and 1, and 75 % of them are col/val loads -- lanes of a warp
-// read 4-8 short row segments that lie 28-216 bytes apart, so every trip re-touches the same 7-15 cache lines -- issued in a
-// dependent chain col -> x.  Here a warp owns a group of G consecutive rows, whose col/val entries are ONE contiguous slice of
-// the CSR arrays: the slice is copied to shared memory with 16-byte cp.async (one tag lookup per 128-byte line, L1 bypassed,
-// asynchronous: the slice of the warp's next group is in flight while the current one is consumed), and the lanes then walk
-// their rows out of shared memory, so the only L1 traffic left is the x gather, which the lanes can issue back to back
-// because the column indices are already on chip.  Per-row summation order is that of k_spmv: results are bit-identical.
-// Groups whose slice exceeds the staging capacity (clusters of hanging-node rows) take the direct path inside the same kernel.
-constexpr int kStWarps = kSpThreads / 32;
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, int src_bytes)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-// the rows of one group, RPG at a time: row (g * RPW + sub) of the group in pass g; cs / vs are indexed by the CSR position
-// minus `base` (shared-memory stage) or by the CSR position itself (direct path, base = 0)
-template <int TPR, int RPG, bool UNIT, class Epi>
-__device__ __forceinline__ void group_rows(const int *cs, const double *vs, int base, const double *__restrict__ x, int p, int pend, long long r0, int num_rows, int skip_len, Epi &epi)
-{
-    constexpr int RPW = 32 / TPR;
-    constexpr int G = RPW * RPG;
-    constexpr int U = TPR == 1 ? 4 : 2; // entries per row and trip in flight
-    const int lane = threadIdx.x % TPR;
-    const int sub = (threadIdx.x & 31) / TPR;
-    int j[RPG], e[RPG];
-    bool skip[RPG];
-    double acc[RPG];
-#pragma unroll
-    for (int g = 0; g < RPG; g++)
-    {
-        const int rg = g * RPW + sub; // row of the group
-        const int s = __shfl_sync(0xffffffffu, p, rg);
-        const int en = __shfl_sync(0xffffffffu, p, (rg + 1) & 31);
-        e[g] = (rg + 1 >= 32) ? pend : en; // lane G of a group with G < 32 rows holds pend itself
-        skip[g] = e[g] - s > skip_len;
-        if (skip[g] || r0 + rg >= num_rows) e[g] = s;
-        j[g] = s + lane - base;
-        e[g] -= base;
-        acc[g] = 0.0;
-    }
-    bool more = false;
-#pragma unroll
-    for (int g = 0; g < RPG; g++) more |= j[g] < e[g];
-    while (more)
-    {
-        int c[RPG][U];
-        double v[RPG][U];
-#pragma unroll
-        for (int g = 0; g < RPG; g++)
-#pragma unroll
-            for (int u = 0; u < U; u++)
-            {
-                const int k = j[g] + u * TPR;
-                const bool on = k < e[g];
-                c[g][u] = on ? cs[k] : -1;
-                v[g][u] = (on && !UNIT) ? vs[k] : 0.0;
-            }
-        double xv[RPG][U];
-#pragma unroll
-        for (int g = 0; g < RPG; g++)
-#pragma unroll
-            for (int u = 0; u < U; u++) xv[g][u] = c[g][u] >= 0 ? x[c[g][u]] : 0.0;
-        more = false;
-#pragma unroll
-        for (int g = 0; g < RPG; g++)
-        {
-#pragma unroll
-            for (int u = 0; u < U; u++)
-                if (c[g][u] >= 0) acc[g] += UNIT ? xv[g][u] : v[g][u] * xv[g][u];
-            j[g] += U * TPR;
-            more |= j[g] < e[g];
-        }
-    }
-#pragma unroll
-    for (int g = 0; g < RPG; g++)
-    {
-#pragma unroll
-        for (int o = TPR / 2; o > 0; o >>= 1) acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], o, TPR);
-        const long long r = r0 + g * RPW + sub;
-        if (r < num_rows && lane == 0 && !skip[g]) epi((int)r, acc[g]);
-    }
-}
-
-template <int TPR, int RPG, bool UNIT, class Epi>
-__global__ void __launch_bounds__(kSpThreads) k_spmv_staged(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, int num_rows, int num_nnz, int cap, int skip_len, Epi epi)
-{
-    constexpr int G = (32 / TPR) * RPG;
-    extern __shared__ __align__(16) unsigned char stage_smem[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    // per warp: two buffers of [cap doubles | cap ints] (UNIT: ints only)
-    const size_t buf_bytes = (size_t)cap * (UNIT ? 4 : 12);
-    unsigned char *mine = stage_smem + (size_t)warp * 2 * buf_bytes;
-    const long long num_groups = ((long long)num_rows + G - 1) / G;
-    const long long stride = (long long)gridDim.x * kStWarps;
-    long long g0 = (long long)blockIdx.x * kStWarps + warp;
-    if (g0 >= num_groups) return; // whole warps leave together
-
-    auto load_ptrs = [&](long long g, int &p, int &pend) {
-        const long long r = g * G + lane;
-        p = ptr[r < num_rows ? r : num_rows];
-        if (G < 32) pend = __shfl_sync(0xffffffffu, p, G);
-        else pend = ptr[(g + 1) * G < num_rows ? (g + 1) * G : num_rows];
-    };
-    // copies the slice [base, pend) of col / val into buffer b; nothing is issued for an oversized slice
-    auto issue = [&](int b, int p, int pend) {
-        const int base = __shfl_sync(0xffffffffu, p, 0) & ~3;
-        const int count = pend - base;
-        if (count <= cap)
-        {
-            unsigned char *dst = mine + (size_t)b * buf_bytes;
-            int *cdst = reinterpret_cast<int *>(dst + (UNIT ? 0 : (size_t)cap * 8));
-            for (int k = 4 * lane; k < count; k += 128)
-            {
-                const int left = num_nnz - (base + k);
-                cp_async16(cdst + k, col + base + k, left >= 4 ? 16 : left * 4);
-            }
-            if (!UNIT)
-            {
-                double *vdst = reinterpret_cast<double *>(dst);
-                for (int k = 2 * lane; k < count; k += 64)
-                {
-                    const int left = num_nnz - (base + k);
-                    cp_async16(vdst + k, val + base + k, left >= 2 ? 16 : left * 8);
-                }
-            }
-        }
-        cp_async_commit();
-    };
-
-    int p_cur, pend_cur, p_nxt = 0, pend_nxt = 0;
-    load_ptrs(g0, p_cur, pend_cur);
-    long long g1 = g0 + stride;
-    if (g1 < num_groups) load_ptrs(g1, p_nxt, pend_nxt);
-    int b = 0;
-    issue(b, p_cur, pend_cur);
-    while (true)
-    {
-        const long long g2 = g1 + stride;
-        int p_n2 = 0, pend_n2 = 0;
-        if (g2 < num_groups) load_ptrs(g2, p_n2, pend_n2); // consumed one trip later
-        if (g1 < num_groups) issue(b ^ 1, p_nxt, pend_nxt);
-        else cp_async_commit();
-        cp_async_wait<1>();
-        __syncwarp();
-        const int base = __shfl_sync(0xffffffffu, p_cur, 0) & ~3;
-        if (pend_cur - base <= cap)
-        {
-            const unsigned char *src = mine + (size_t)b * buf_bytes;
-            group_rows<TPR, RPG, UNIT>(reinterpret_cast<const int *>(src + (UNIT ? 0 : (size_t)cap * 8)), reinterpret_cast<const double *>(src), base, x, p_cur, pend_cur, g0 * G, num_rows, skip_len, epi);
-        }
-        else
-            group_rows<TPR, RPG, UNIT>(col, val, 0, x, p_cur, pend_cur, g0 * G, num_rows, skip_len, epi);
-        __syncwarp();
-        if (g1 >= num_groups) break;
-        g0 = g1; g1 = g2;
-        p_cur = p_nxt; pend_cur = pend_nxt;
-        p_nxt = p_n2; pend_nxt = pend_n2;
-        b ^= 1;
-    }
-}
-
 // one entry per row (ptr == NULL): out = epi(row, [val] x[col[row]])  -- Q of a conforming region
 template <bool UNIT, class Epi>
 __global__ void __launch_bounds__(256) k_spmv_single(const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, int row_start, int num_rows, Epi epi)
@@ -285,60 +114,20 @@ __global__ void __launch_bounds__(256) k_spmv_single(const int *__restrict__ col
     for (long long r = row_start + (long long)blockIdx.x * blockDim.x + threadIdx.x; r < row_start + num_rows; r += stride) epi((int)r, UNIT ? x[col[r]] : val[r] * x[col[r]]);
 }
 
-static int g_spmv_variant = -1; // -1: read PRFDD_SPMV_VARIANT on first use; 0: row-group kernels only; 1: staged where the descriptor allows
-static int g_spmv_ctas = 0;     // CTAs per SM of the staged kernel (0: from shared memory)
-static int spmv_variant()
-{
-    if (g_spmv_variant < 0)
-    {
-        const char *e = getenv("PRFDD_SPMV_VARIANT");
-        g_spmv_variant = e ? atoi(e) : 1;
-        const char *c = getenv("PRFDD_SPMV_CTAS");
-        g_spmv_ctas = c ? atoi(c) : 0;
-    }
-    return g_spmv_variant;
-}
-
-template <int TPR, int RPG, bool UNIT, class Epi>
-static void launch_staged(const prfdd_csr_matrix &A, const double *x, cudaStream_t st, Epi epi)
-{
-    constexpr int G = (32 / TPR) * RPG;
-    const size_t smem = (size_t)kStWarps * 2 * A.stage_cap * (UNIT ? 4 : 12);
-    static size_t smem_set = 0; // per instantiation
-    if (smem > smem_set)
-    {
-        cudaFuncSetAttribute(k_spmv_staged<TPR, RPG, UNIT, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        smem_set = smem;
-    }
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
-    per_sm = per_sm < 1 ? 1 : per_sm > 6 ? 6 : per_sm;
-    if (g_spmv_ctas > 0 && g_spmv_ctas < per_sm) per_sm = g_spmv_ctas;
-    const long long groups = ((long long)A.num_rows + G - 1) / G;
-    long long grid = (groups + kStWarps - 1) / kStWarps;
-    const long long cap = (long long)num_sms() * per_sm;
-    if (grid > cap) grid = cap;
-    const int skip_len = A.num_long_rows > 0 ? A.long_row_threshold : 0x7fffffff;
-    k_spmv_staged<TPR, RPG, UNIT><<<(int)grid, kSpThreads, smem, st>>>(A.ptr, A.col, A.val, x, A.num_rows, A.num_nnz, A.stage_cap, skip_len, epi);
-}
-
 template <int TPR, bool UNIT, class Epi>
-static void launch_spmv(const prfdd_csr_matrix &A, const double *x, int row_start, int num_rows, cudaStream_t st, Epi epi)
+static void launch_spmv(const prfdd_csr_matrix &A, const double *x, int row_start, int num_rows, bool lr, cudaStream_t st, Epi epi)
 {
-    const bool lr = x && row_start == 0 && TPR < 32 && A.num_long_rows > 0 && A.long_rows;
-    if constexpr (!UNIT)
-    {
-        // two rows per sub-warp once the matrix is large enough to fill the machine with half as many warps
-        // (AMG level 1 of the 16^3 N=7 problem, 27 entries/row: 54.9 -> 49.1 us; profiles/r1_notes.txt)
-        const bool two = TPR >= 4 && (long long)num_rows * TPR >= (1ll << 21);
-        const int grid = stream_grid((long long)num_rows * TPR / (two ? 2 : 1), kSpThreads, 1, 16);
-        const int skip_len = lr ? A.long_row_threshold : 0x7fffffff;
-        if (two) k_spmv<TPR, 2><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
-        else k_spmv<TPR, 1><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
-    }
+    // two rows per sub-warp once the matrix is large enough to fill the machine with half as many warps
+    // (AMG level 1 of the 16^3 N=7 problem, 27 entries/row: 54.9 -> 49.1 us; profiles/r1_notes.txt)
+    const bool two = TPR >= 4 && (long long)num_rows * TPR >= (1ll << 21);
+    const int grid = stream_grid((long long)num_rows * TPR / (two ? 2 : 1), kSpThreads, 1, 16);
+    const int skip_len = lr ? A.long_row_threshold : 0x7fffffff;
+    if (two) k_spmv<TPR, 2, UNIT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
+    else k_spmv<TPR, 1, UNIT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
     if (lr) k_spmv_long<UNIT><<<(A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
 }
 
-// dispatch on the descriptor.  `heavy`: epilogues of the V-cycle get every staged shape; the others a reduced set
+// dispatch on the descriptor
 template <class Epi>
 static int spmv(const prfdd_csr_matrix &A, const double *x, int row_start, int num_rows, cudaStream_t st, Epi epi)
 {
@@ -353,47 +142,32 @@ static int spmv(const prfdd_csr_matrix &A, const double *x, int row_start, int n
         else k_spmv_single<false><<<stream_grid(num_rows, 256, 2, 8), 256, 0, st>>>(A.col, A.val, x, row_start, num_rows, epi);
         return launched();
     }
-    int tpr = A.threads_per_row > 0 ? A.threads_per_row : 4;
+    const int tpr = A.threads_per_row > 0 ? A.threads_per_row : 4;
     const bool lr = x && row_start == 0 && tpr < 32 && A.num_long_rows > 0 && A.long_rows;
-    const bool staged = x && row_start == 0 && num_rows == A.num_rows && A.stage_cap > 0 && A.num_nnz > 0 && (spmv_variant() == 1 || unit);
-    if (unit && !staged) return -9; // a matrix without values needs a staging plan (prfdd_csr_plan)
-    if (staged)
+    if (unit)
     {
-        const int rpg = A.stage_rows_per_lane_group;
-        bool done = true;
-#define PRFDD_STAGED(T, R)                                                   \
-    if (unit) launch_staged<T, R, true>(A, x, st, epi);                      \
-    else launch_staged<T, R, false>(A, x, st, epi);
-        if (tpr == 1) { PRFDD_STAGED(1, 1) }
-        else if (tpr == 2) { PRFDD_STAGED(2, 1) }
-        else if (tpr == 4 && rpg == 2) { PRFDD_STAGED(4, 2) }
-        else if (tpr == 4) { PRFDD_STAGED(4, 1) }
-        else if (tpr == 8 && rpg == 2) { PRFDD_STAGED(8, 2) }
-        else if (tpr == 8) { PRFDD_STAGED(8, 1) }
-        else if (tpr == 16) { PRFDD_STAGED(16, 1) }
-        else done = false;
-#undef PRFDD_STAGED
-        if (done)
+        // matrices without values are Q^T-like: short rows
+        switch (tpr)
         {
-            if (lr)
-            {
-                if (unit) k_spmv_long<true><<<(A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
-                else k_spmv_long<false><<<(A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
-                prfdd_launch_count_add(1);
-            }
-            return launched();
+        case 1: launch_spmv<1, true>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 2: launch_spmv<2, true>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 4: launch_spmv<4, true>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 8: launch_spmv<8, true>(A, x, row_start, num_rows, lr, st, epi); break;
+        default: return -6;
         }
-        if (unit) return -9;
     }
-    switch (tpr)
+    else
     {
-    case 1: launch_spmv<1, false>(A, x, row_start, num_rows, st, epi); break;
-    case 2: launch_spmv<2, false>(A, x, row_start, num_rows, st, epi); break;
-    case 4: launch_spmv<4, false>(A, x, row_start, num_rows, st, epi); break;
-    case 8: launch_spmv<8, false>(A, x, row_start, num_rows, st, epi); break;
-    case 16: launch_spmv<16, false>(A, x, row_start, num_rows, st, epi); break;
-    case 32: launch_spmv<32, false>(A, x, row_start, num_rows, st, epi); break;
-    default: return -6;
+        switch (tpr)
+        {
+        case 1: launch_spmv<1, false>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 2: launch_spmv<2, false>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 4: launch_spmv<4, false>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 8: launch_spmv<8, false>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 16: launch_spmv<16, false>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 32: launch_spmv<32, false>(A, x, row_start, num_rows, lr, st, epi); break;
+        default: return -6;
+        }
     }
     if (lr) prfdd_launch_count_add(1);
     return launched();
@@ -520,8 +294,6 @@ int prfdd_csr_plan(prfdd_csr_matrix *A, const int *ptr_host, int *long_rows_host
     A->long_rows = nullptr;
     A->num_long_rows = 0;
     A->long_row_threshold = 0;
-    A->stage_cap = 0;
-    A->stage_rows_per_lane_group = 1;
     const double avg = (double)nnz / (n > 0 ? n : 1);
     const int tpr = lanes_per_row(avg, n);
     A->threads_per_row = tpr;
@@ -544,41 +316,7 @@ int prfdd_csr_plan(prfdd_csr_matrix *A, const int *ptr_host, int *long_rows_host
             if (ptr_host[r + 1] - ptr_host[r] > threshold) long_rows_host[listed++] = r;
         A->long_row_threshold = threshold;
     }
-    // staging plan: G consecutive rows per warp and trip; the capacity covers (nearly) every group
-    const int rpg = (tpr >= 4 && tpr < 16 && avg <= 40.0) ? 2 : 1;
-    if (tpr <= 16)
-    {
-        const int G = (32 / tpr) * rpg;
-        const long long groups = ((long long)n + G - 1) / G;
-        std::vector<int> cnt((size_t)groups);
-        for (long long g = 0; g < groups; g++)
-        {
-            const long long r0 = g * G, r1 = std::min<long long>(r0 + G, n);
-            cnt[(size_t)g] = ptr_host[r1] - (ptr_host[r0] & ~3);
-        }
-        std::vector<int> sorted(cnt);
-        const size_t k = (size_t)std::min<long long>(groups - 1, (long long)std::ceil(0.995 * groups));
-        std::nth_element(sorted.begin(), sorted.begin() + k, sorted.end());
-        const int p995 = sorted[k];
-        const int mx = *std::max_element(cnt.begin(), cnt.end());
-        constexpr int kCapMax = 544; // 2 CTAs of 8 warps per SM: 8 * 2 * 544 * 12 B = 102 KB each
-        int cap = (mx <= kCapMax || mx <= p995 + p995 / 4) ? mx : p995;
-        cap = ((std::max(cap, 32) + 31) / 32) * 32;
-        if (cap <= kCapMax)
-        {
-            A->stage_cap = cap;
-            A->stage_rows_per_lane_group = rpg;
-        }
-    }
     return listed;
-}
-
-int prfdd_csr_set_spmv_variant(int variant, int ctas_per_sm)
-{
-    spmv_variant();
-    g_spmv_variant = variant ? 1 : 0;
-    g_spmv_ctas = ctas_per_sm;
-    return 0;
 }
 
 // ---- descriptor entry points ----------------------------------------------------------------

@@ -293,24 +293,29 @@ def test_csr_ragged_rows_and_row_ranges(G, tpr, nr):
     assert lib.prfdd_csr_residual(off(out2, r0, 8), off(dptr, r0, 4), G.p(dcol), G.p(dval), G.p(du), off(df, r0, 8), C.c_int(nr - r0), C.c_int(8), G.stream()) == 0
     G.sync(); assert np.abs(G.host(out2) - (f - ref)).max() <= tol
     assert lib.prfdd_csr_multiply(G.p(out), G.p(dptr), G.p(dcol), G.p(dval), G.p(du), C.c_int(nr), C.c_int(3), G.stream()) == -6
-    # descriptor with the library's plan: listed long rows go to the warp-per-row launch, the rest to the staged / row-group kernel
-    for variant in (0, 1):
-        assert lib.prfdd_csr_set_spmv_variant(C.c_int(variant), C.c_int(0)) == 0
-        D, keep = csr_descriptor(G, ptr, dptr, dcol, dval)
-        out3 = G.dev(np.full(nr, 7.0))
-        assert lib.prfdd_csrm_residual(G.p(out3), C.byref(D), G.p(du), G.p(df), G.stream()) == 0
-        G.sync(); assert np.abs(G.host(out3) - (f - ref)).max() <= tol
-    assert lib.prfdd_csr_set_spmv_variant(C.c_int(1), C.c_int(0)) == 0
+    # descriptor with the library's plan: the listed long rows go to the warp-per-row launch, the rest to the row-group kernel
+    D, keep = csr_descriptor(G, ptr, dptr, dcol, dval)
+    out3 = G.dev(np.full(nr, 7.0))
+    assert lib.prfdd_csrm_residual(G.p(out3), C.byref(D), G.p(du), G.p(df), G.stream()) == 0
+    G.sync(); assert np.abs(G.host(out3) - (f - ref)).max() <= tol
+    # a forced list (threshold 24) on a shorter row range: listed rows beyond the range are left alone
+    T = 24
+    rows = np.flatnonzero(lens > T).astype(np.int32)
+    keep2 = G.dev(rows)
+    D.long_rows, D.num_long_rows, D.long_row_threshold = keep2.data_ptr(), len(rows), T
+    out4 = G.dev(np.full(nr, 7.0))
+    assert lib.prfdd_csrm_residual(G.p(out4), C.byref(D), G.p(du), G.p(df), G.stream()) == 0
+    G.sync(); assert np.abs(G.host(out4) - (f - ref)).max() <= tol
 
 
 class CsrDesc(C.Structure):
     """prfdd_csr_matrix (include/prfdd_b200.h)"""
     _fields_ = [("ptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p), ("num_rows", C.c_int), ("num_nnz", C.c_int), ("threads_per_row", C.c_int),
-                ("long_rows", C.c_void_p), ("num_long_rows", C.c_int), ("long_row_threshold", C.c_int), ("stage_rows_per_lane_group", C.c_int), ("stage_cap", C.c_int)]
+                ("long_rows", C.c_void_p), ("num_long_rows", C.c_int), ("long_row_threshold", C.c_int)]
 
 
-def csr_descriptor(G, ptr_host, dptr, dcol, dval, tpr=None, rpg=None):
-    """descriptor planned by prfdd_csr_plan; tpr / rpg override the planned launch shape (the capacity is then re-derived here)"""
+def csr_descriptor(G, ptr_host, dptr, dcol, dval, tpr=None):
+    """descriptor planned by prfdd_csr_plan; tpr overrides the planned lanes per row"""
     nr = len(ptr_host) - 1
     D = CsrDesc()
     D.ptr, D.col, D.val = dptr.data_ptr(), dcol.data_ptr(), (dval.data_ptr() if dval is not None else None)
@@ -323,61 +328,12 @@ def csr_descriptor(G, ptr_host, dptr, dcol, dval, tpr=None, rpg=None):
         keep = G.dev(rows[:cnt].copy())
         D.long_rows, D.num_long_rows = keep.data_ptr(), cnt
     if tpr is not None:
-        D.threads_per_row, D.stage_rows_per_lane_group = tpr, rpg
-        g = (32 // tpr) * rpg
-        starts = np.arange(0, nr, g)
-        ends = np.minimum(starts + g, nr)
-        cap = int((ptr_host[ends] - (ptr_host[starts] & ~3)).max()) if nr else 0
-        D.stage_cap = min(((max(cap, 32) + 31) // 32) * 32, 544)
+        D.threads_per_row = tpr
     return D, keep
 
 
-@pytest.mark.parametrize("shape", [(1, 1), (2, 1), (4, 1), (4, 2), (8, 1), (8, 2), (16, 1)])
-def test_csr_staged_kernel_every_shape(G, shape):
-    """the warp-staged SpMV (cp.async slices of row groups, double-buffered) against the oracle's scalar loop and, bit for bit, against
-    the row-group kernel: every (lanes per row, rows per lane group) shape, ragged rows, groups larger than the staging capacity (direct
-    path inside the kernel), a matrix end that is not a multiple of the 16-byte copies, every epilogue of the V-cycle"""
-    import scipy.sparse as sp
-    tpr, rpg = shape
-    rng = np.random.default_rng(7 * tpr + rpg)
-    lib, L = G.lib, oc.lib()
-    nr = 50021
-    lens = rng.integers(0, 3 * tpr + 6, nr)
-    lens[rng.integers(0, nr, 60)] = rng.integers(100, 900, 60)      # oversized groups
-    lens[:2] = [0, 5]; lens[-1] = 3
-    ptr = np.zeros(nr + 1, np.int32); ptr[1:] = np.cumsum(lens)
-    nnz = int(ptr[-1])
-    row_of = np.repeat(np.arange(nr), lens)
-    col = np.clip(row_of + rng.integers(-2000, 2000, nnz), 0, nr - 1).astype(np.int32)
-    val = rng.standard_normal(nnz)
-    x = rng.standard_normal(nr); f = rng.standard_normal(nr); r = rng.standard_normal(nr); ds = rng.uniform(0.5, 2.0, nr)
-    dptr, dcol, dval, dx, df, dr, dds = (G.dev(a) for a in (ptr, col, val, x, f, r, ds))
-    ref = np.zeros(nr); L.o_csr_multiply(P(ref), P(ptr), P(col), P(val), P(x), C.c_int(nr))
-    tol = 8e-15 * (np.abs(sp.csr_matrix((val, col, ptr), shape=(nr, nr))) @ np.abs(x)).max()
-    D, keep = csr_descriptor(G, ptr, dptr, dcol, dval, tpr, rpg)
-    assert D.stage_cap > 0
-    outs = {}
-    for variant in (0, 1):
-        assert lib.prfdd_csr_set_spmv_variant(C.c_int(variant), C.c_int(0)) == 0
-        y, v, rr, tt, uu, t2 = (G.dev(np.full(nr, 3.0)) for _ in range(6))
-        assert lib.prfdd_csrm_multiply(G.p(y), C.byref(D), G.p(dx), G.stream()) == 0
-        assert lib.prfdd_csrm_residual(G.p(v), C.byref(D), G.p(dx), G.p(df), G.stream()) == 0
-        assert lib.prfdd_csrm_cheby_residual(G.p(rr), G.p(tt), C.byref(D), G.p(dx), G.p(df), G.p(dds), C.c_double(0.3), G.stream()) == 0
-        assert lib.prfdd_csrm_cheby_step(G.p(uu), G.p(t2), C.byref(D), G.p(dx), G.p(dr), G.p(dds), C.c_double(0.7), C.c_int(1), C.c_int(0), G.stream()) == 0
-        assert lib.prfdd_csrm_cheby_step(G.p(uu), G.p(t2), C.byref(D), G.p(dx), G.p(dr), G.p(dds), C.c_double(0.7), C.c_int(0), C.c_int(0), G.stream()) == 0
-        assert lib.prfdd_csrm_matvec(G.p(y), C.byref(D), G.p(dx), C.c_double(2.0), C.c_double(1.0), G.stream()) == 0
-        G.sync()
-        outs[variant] = [G.host(t) for t in (y, v, rr, tt, uu, t2)]
-    assert lib.prfdd_csr_set_spmv_variant(C.c_int(1), C.c_int(0)) == 0
-    for a, b in zip(outs[0], outs[1]):
-        assert np.array_equal(a, b)                         # same per-row summation order
-    assert np.abs(outs[1][0] - 3.0 * ref).max() <= 3 * tol  # y = A x, then y = 2 A x + y
-    assert np.abs(outs[1][1] - (f - ref)).max() <= tol
-    assert np.abs(outs[1][2] - ds * (f - ref)).max() <= 2 * tol
-    assert np.abs(outs[1][5] - ds * (0.7 * r + ds * ref)).max() <= 4 * tol
-
-
-def test_csr_unit_values_and_index_map(G):
+@pytest.mark.parametrize("tpr", [1, 2, 4, 8])
+def test_csr_unit_values_and_index_map(G, tpr):
     """val == NULL (all stored values 1.0: Q^T of a conforming region) and ptr == NULL (one entry per row: Q) against the CSR product"""
     rng = np.random.default_rng(3)
     lib, L = G.lib, oc.lib()
@@ -390,14 +346,13 @@ def test_csr_unit_values_and_index_map(G):
     ones = np.ones(npts)
     dptr, dcol, du, dw = (G.dev(a) for a in (ptr, col, u, w))
     ref = np.zeros(nn); L.o_csr_multiply(P(ref), P(ptr), P(col), P(ones), P(u), C.c_int(nn))
-    D, keep = csr_descriptor(G, ptr, dptr, dcol, None)
-    assert D.stage_cap > 0
+    D, keep = csr_descriptor(G, ptr, dptr, dcol, None, tpr)
     out = G.dev(np.full(nn, 5.0))
     assert lib.prfdd_csrm_multiply_weight(G.p(out), C.byref(D), G.p(du), G.p(dw), G.stream()) == 0
     G.sync(); assert np.abs(G.host(out) - ref * w).max() <= 1e-14 * np.abs(ref).max()
     # Q: one entry per row, index map
-    Q = CsrDesc(); Q.col = G.dev(node).data_ptr(); Q.num_rows = npts; Q.num_nnz = npts; Q.threads_per_row = 1
-    keep2 = G.dev(node); Q.col = keep2.data_ptr()
+    keep2 = G.dev(node)
+    Q = CsrDesc(); Q.col = keep2.data_ptr(); Q.num_rows = npts; Q.num_nnz = npts; Q.threads_per_row = 1
     nodes = rng.standard_normal(nn); dn = G.dev(nodes)
     out2 = G.dev(np.zeros(npts))
     assert lib.prfdd_csrm_multiply(G.p(out2), C.byref(Q), G.p(dn), G.stream()) == 0
