@@ -368,6 +368,11 @@ int prfdd_halo_build_lists(int proc_id, int num_procs, const long long *ids, con
 typedef struct prfdd_amg_host prfdd_amg_host;
 int prfdd_amg_host_setup(prfdd_amg_host **h, int n, const int *ptr, const int *col, const double *val, int cheby_order,
                          int max_coarse_size);
+/* coarsening: 0 = PMIS with hashed measures, 1 = HMIS (on one process: the first Ruge-Stueben pass, first-in first-out among
+ * equal measures) -- what coarsen type 10 of the reference selects (subdomain.tpp:1853); -1 = the library default
+ * (PRFDD_AMG_COARSENING=pmis|hmis, else the value DESIGN.md names) */
+int prfdd_amg_host_setup_ex(prfdd_amg_host **h, int n, const int *ptr, const int *col, const double *val, int cheby_order,
+                            int max_coarse_size, int coarsening);
 int prfdd_amg_host_destroy(prfdd_amg_host *h);
 int prfdd_amg_host_num_levels(const prfdd_amg_host *h);
 /* sizes[0..3] = rows of A_l, nnz of A_l, columns of P_l (0 on the last level), nnz of P_l */
@@ -404,6 +409,7 @@ typedef struct prfdd_options
     int outer_max_iterations; /* 500 (domain.hpp:114) */
     int outer_num_vectors;    /* 20 (domain.hpp:113) */
     int verbose;              /* print the reference's "Iter ..." lines on rank 0 */
+    int amg_coarsening;       /* -1 library default, 0 PMIS, 1 HMIS (HYPRE coarsen type 10, subdomain.tpp:1853) */
 } prfdd_options;
 
 void prfdd_options_default(prfdd_options *opt);

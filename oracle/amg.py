@@ -9,8 +9,11 @@ and 3480-3549) and the Chebyshev-smoothed V-cycle of subdomain.tpp:3987-4159.
 setup cannot be reproduced bit for bit.  What is restated here is the *published algorithm family* HYPRE's
 defaults select, made deterministic:
   * classical strength of connection, theta = 0.25 (negative couplings)            [Ruge-Stueben 1987]
-  * PMIS coarsening (the parallel-independent-set half of HMIS, coarsen type 10)     [De Sterck, Yang, Heys 2006]
-    with hashed (not random) tie-breaking measures
+  * coarsening, selectable (set_coarsening):
+      "pmis"  PMIS (the parallel-independent-set half of HMIS)                       [De Sterck, Yang, Heys 2006]
+              with hashed (not random) tie-breaking measures
+      "hmis"  HMIS, coarsen type 10, the value the reference requests (subdomain.tpp:1853, default of 3480-3489): on one
+              process it is the FIRST pass of the Ruge-Stueben colouring alone (oracle/amg_rs.c), ties first-in first-out
   * extended+i interpolation (interp type 6), truncated to P_max = 4 per row         [De Sterck, Falgout, Nolting, Yang 2008]
   * Galerkin coarse operators R A P with R = P^T; coarsest level solved exactly (hypre_GaussElimSolve)
   * Chebyshev smoother, hypre's scaled variant: ds = 1/sqrt(diag), spectrum of ds A ds estimated by
@@ -21,6 +24,7 @@ The product implements the same setup in C++ (csrc/host/amg.hpp); tests compare 
 (C/F splittings exactly, matrices to 1e-12).
 """
 import ctypes as C
+import os
 import numpy as np
 import scipy.sparse as sp
 
@@ -59,6 +63,26 @@ def strength(A, theta=0.25):
     S = sp.csr_matrix((np.ones(int(strong.sum()), dtype=np.int8), (rows[strong], A.indices[strong])), shape=A.shape)
     S.sort_indices()
     return S
+
+
+COARSENING = os.environ.get("PRFDD_AMG_COARSENING", "hmis").lower()   # default: what the reference requests from HYPRE
+
+
+def set_coarsening(name):
+    """ "pmis" or "hmis" for every Hierarchy built from now on"""
+    global COARSENING
+    assert name in ("pmis", "hmis")
+    COARSENING = name
+
+
+def rs_first_pass(S):
+    """HMIS on one process = first Ruge-Stueben pass (oracle/amg_rs.c).  Returns cf: +1 C, -1 F."""
+    S = S.tocsr(); S.sort_indices()
+    n = S.shape[0]
+    cf = np.zeros(n, dtype=np.int8)
+    ptr, col = S.indptr.astype(np.int32), S.indices.astype(np.int32)
+    _c.lib().oracle_rs_first_pass(C.c_int(n), P_(ptr), P_(col), P_(cf))
+    return cf
 
 
 def pmis(S, salt):
@@ -243,6 +267,15 @@ def cheby_coefs(lower, upper, order):
     return np.ascontiguousarray(p[:order])
 
 
+def _csr_arrays(M):
+    """int32 / float64 views of a scipy CSR matrix for the C kernels, converted once per matrix (not per call)"""
+    c = getattr(M, "_oracle_arrays", None)
+    if c is None:
+        c = (np.ascontiguousarray(M.indptr, dtype=np.int32), np.ascontiguousarray(M.indices, dtype=np.int32), np.ascontiguousarray(M.data, dtype=np.float64))
+        M._oracle_arrays = c
+    return c
+
+
 class Level:
     pass
 
@@ -264,7 +297,7 @@ class Hierarchy:
             if L.n <= max_coarse or l + 1 >= max_levels:
                 break
             S = strength(A, theta)
-            cf = pmis(S, salt=l)
+            cf = rs_first_pass(S) if COARSENING.startswith("h") else pmis(S, salt=l)
             nc = int((cf == 1).sum())
             if nc == 0 or nc == L.n:
                 break
@@ -286,7 +319,7 @@ class Hierarchy:
         """scaled_residual + polynomial_evaluation x (order-1) + update_field (subdomain.tpp:3652-3657), host branches."""
         K = _c.lib()
         A = L.A
-        ptr, col, val = A.indptr.astype(np.int32), A.indices.astype(np.int32), np.ascontiguousarray(A.data)
+        ptr, col, val = _csr_arrays(A)
         n = L.n
         r = np.zeros(n); w = np.zeros(n); v = np.zeros(n)
         k = self.cheby_order
@@ -298,7 +331,7 @@ class Hierarchy:
     @staticmethod
     def _matvec(M, y, x, alpha, beta):
         K = _c.lib()
-        ptr, col, val = M.indptr.astype(np.int32), M.indices.astype(np.int32), np.ascontiguousarray(M.data)
+        ptr, col, val = _csr_arrays(M)
         K.o_amg_matvec(P_(y), P_(ptr), P_(col), P_(val), P_(x), C.c_double(alpha), C.c_double(beta), C.c_int(M.shape[0]))
 
     def vcycle(self, f0, num_vcycles=1):

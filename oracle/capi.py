@@ -16,20 +16,38 @@ i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
 def build():
-    """Compile liboracle.so (and oracle/_ref when /root/reference is mounted)."""
-    subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so"])
+    """Compile liboracle.so, liboracle_omp.so (and oracle/_ref when /root/reference is mounted)."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so", "liboracle_omp.so"])
     if os.path.isdir("/root/reference"):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+_threads = 1
+
+
+def set_threads(n):
+    """n > 1: the @outer loops of every kernel run on n host threads (liboracle_omp.so: the same source compiled with OpenMP;
+    the OCCA OpenMP analogue of config.hpp:34-36); bit-identical results.  Call before the first kernel call."""
+    global _lib, _threads
+    n = max(1, int(n))
+    if (n > 1) != (_threads > 1):
+        _lib = None
+    _threads = n
+    if n > 1:
+        os.environ["OMP_NUM_THREADS"] = str(n)
+        lib()
 
 
 def lib():
     global _lib
     if _lib is None:
-        path = os.path.join(HERE, "liboracle.so")
+        name = "liboracle_omp.so" if _threads > 1 else "liboracle.so"
+        path = os.path.join(HERE, name)
         if not os.path.exists(path):
             build()
         _lib = C.CDLL(path)
         _lib.oracle_hgll.restype = C.c_double
+        _lib.o_serial_sum.restype = C.c_double
     return _lib
 
 

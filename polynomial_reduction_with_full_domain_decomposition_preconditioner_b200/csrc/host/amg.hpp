@@ -276,6 +276,96 @@ inline std::vector<signed char> pmis(int n, const std::vector<int> &Sptr, const 
     return cf;
 }
 
+// HMIS on one process.  The reference asks for coarsen type 10 (subdomain.tpp:1853; HYPRE's default for the second setup,
+// 3480-3489): HMIS = the FIRST pass of the classical Ruge-Stueben colouring on the points without off-process connections,
+// then PMIS on what is left.  Every hierarchy here lives on one process (MPI_COMM_SELF), so nothing is left: HMIS is the
+// first Ruge-Stueben pass alone (no second pass; F-F connections without a common C point are allowed, as in HMIS).
+// Measure lambda_i = |S^T_i|; repeatedly take a point of maximal measure as C, make the undecided points that strongly depend
+// on it F, raise the measure of the undecided points each new F point depends on, lower the measure of the undecided points
+// the new C point depends on.  Points of equal measure are served first-in first-out (a point that changes measure
+// re-enters at the tail of its new list; the initial order is the index order), which makes the splitting deterministic.
+// Points nobody depends on start as F.  cf = +1 (C) / -1 (F).
+inline std::vector<signed char> rs_first_pass(int n, const std::vector<int> &Sptr, const std::vector<int> &Scol)
+{
+    std::vector<int> Tptr(n + 1, 0), Tcol(Scol.size());
+    for (int c : Scol) Tptr[c + 1]++;
+    for (int i = 0; i < n; i++) Tptr[i + 1] += Tptr[i];
+    {
+        std::vector<int> next(Tptr.begin(), Tptr.end() - 1);
+        for (int i = 0; i < n; i++)
+            for (int j = Sptr[i]; j < Sptr[i + 1]; j++) Tcol[next[Scol[j]]++] = i;
+    }
+    std::vector<int> measure(n);
+    int max_measure = 0;
+    for (int i = 0; i < n; i++) { measure[i] = Tptr[i + 1] - Tptr[i]; max_measure = std::max(max_measure, measure[i]); }
+    const int nbuckets = 2 * max_measure + 2; // a measure grows by at most |S^T_i|
+    std::vector<int> head(nbuckets, -1), tail(nbuckets, -1), nxt(n, -1), prv(n, -1);
+    auto push_back = [&](int i) {
+        const int m = measure[i];
+        prv[i] = tail[m]; nxt[i] = -1;
+        if (tail[m] >= 0) nxt[tail[m]] = i; else head[m] = i;
+        tail[m] = i;
+    };
+    auto unlink = [&](int i) {
+        const int m = measure[i];
+        if (prv[i] >= 0) nxt[prv[i]] = nxt[i]; else head[m] = nxt[i];
+        if (nxt[i] >= 0) prv[nxt[i]] = prv[i]; else tail[m] = prv[i];
+    };
+    std::vector<signed char> cf(n, 0);
+    int top = 0;
+    for (int i = 0; i < n; i++)
+    {
+        if (measure[i] == 0) { cf[i] = -1; continue; }
+        push_back(i);
+        top = std::max(top, measure[i]);
+    }
+    while (true)
+    {
+        while (top > 0 && head[top] < 0) top--;
+        if (top <= 0) break;
+        const int i = head[top];
+        unlink(i);
+        cf[i] = 1;
+        for (int jj = Tptr[i]; jj < Tptr[i + 1]; jj++)
+        {
+            const int j = Tcol[jj];
+            if (cf[j] != 0) continue;
+            unlink(j);
+            cf[j] = -1;
+            for (int kk = Sptr[j]; kk < Sptr[j + 1]; kk++)
+            {
+                const int k = Scol[kk];
+                if (cf[k] != 0) continue;
+                unlink(k);
+                measure[k]++;
+                push_back(k);
+                top = std::max(top, measure[k]);
+            }
+        }
+        for (int jj = Sptr[i]; jj < Sptr[i + 1]; jj++)
+        {
+            const int j = Scol[jj];
+            if (cf[j] != 0) continue;
+            unlink(j);
+            measure[j]--;
+            if (measure[j] <= 0) cf[j] = -1; // nobody undecided depends on it any more
+            else push_back(j);
+        }
+    }
+    return cf;
+}
+
+enum Coarsening { COARSEN_PMIS = 0, COARSEN_HMIS = 1 };
+inline int default_coarsening()
+{
+    static const int c = [] {
+        const char *e = getenv("PRFDD_AMG_COARSENING");
+        if (!e) return (int)COARSEN_HMIS; // what the reference requests from HYPRE
+        return (e[0] == 'p' || e[0] == 'P' || e[0] == '0') ? (int)COARSEN_PMIS : (int)COARSEN_HMIS;
+    }();
+    return c;
+}
+
 // extended+i interpolation, truncated to pmax entries per row (largest |w|, ties to the lower column), rescaled
 inline HostCSR interp_extpi(const HostCSR &A, const std::vector<int> &Sptr, const std::vector<int> &Scol, const std::vector<signed char> &cf, int pmax)
 {
@@ -609,6 +699,7 @@ class Hierarchy
   public:
     std::vector<Level> levels;
     int cheby_order = 2;
+    int coarsening = -1; // COARSEN_PMIS / COARSEN_HMIS; -1: PRFDD_AMG_COARSENING or the default
     std::vector<double> Ainv_hst;
     dev::memory Ainv;
     // Collapsed coarse levels.  Below the first level the V-cycle always starts from a zero guess and the Chebyshev coefficients are
@@ -641,7 +732,8 @@ class Hierarchy
             std::vector<int> Sptr, Scol;
             strength(L.A, theta, Sptr, Scol);
             double t2 = now();
-            L.cf = pmis(L.n, Sptr, Scol, (uint64_t)l);
+            const int how = coarsening >= 0 ? coarsening : default_coarsening();
+            L.cf = how == COARSEN_HMIS ? rs_first_pass(L.n, Sptr, Scol) : pmis(L.n, Sptr, Scol, (uint64_t)l);
             double t3 = now();
             int nc = 0;
             for (auto c : L.cf) nc += (c == 1);

@@ -91,6 +91,7 @@ void prfdd_options_default(prfdd_options *o)
     o->outer_max_iterations = 500;
     o->outer_num_vectors = 20;
     o->verbose = 0;
+    o->amg_coarsening = -1;
 }
 
 int prfdd_solver_create(prfdd_solver **out, const char *directory, const prfdd_options *opt, prfdd_stream_t stream)
@@ -333,6 +334,11 @@ struct prfdd_amg_host
 
 int prfdd_amg_host_setup(prfdd_amg_host **h, int n, const int *ptr, const int *col, const double *val, int cheby_order, int max_coarse_size)
 {
+    return prfdd_amg_host_setup_ex(h, n, ptr, col, val, cheby_order, max_coarse_size, -1);
+}
+
+int prfdd_amg_host_setup_ex(prfdd_amg_host **h, int n, const int *ptr, const int *col, const double *val, int cheby_order, int max_coarse_size, int coarsening)
+{
     try
     {
         amg::HostCSR A;
@@ -341,6 +347,7 @@ int prfdd_amg_host_setup(prfdd_amg_host **h, int n, const int *ptr, const int *c
         A.col.assign(col, col + ptr[n]);
         A.val.assign(val, val + ptr[n]);
         prfdd_amg_host *o = new prfdd_amg_host();
+        o->H.coarsening = coarsening;
         o->H.setup(std::move(A), cheby_order, max_coarse_size, 0.25, 4, 25, /*on_device=*/false);
         *h = o;
         return 0;

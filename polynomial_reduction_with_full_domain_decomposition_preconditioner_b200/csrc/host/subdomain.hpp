@@ -473,6 +473,7 @@ void Subdomain<DType>::build_single_rank(std::map<int, std::unique_ptr<Domain<DT
         setup_mark("region, Q, weights (1 rank)");
         assemble_low_order_fem();
         setup_mark("low-order FEM assembly");
+        amg_fem.coarsening = opt.amg_coarsening;
         amg_fem.setup(A_fem_hst, cheby_order);
         setup_mark("AMG #2 (hierarchy, upload, collapsed coarse levels)");
     }

@@ -412,6 +412,7 @@ void Subdomain<DType>::build_multi_rank(std::map<int, std::unique_ptr<Domain<DTy
     }
     // BoomerAMG #1 stand-in: coarsen to a single dof (tpp:1851-1858)
     setup_mark("region Q, operators, global N=1 matrix");
+    amg_coarse.coarsening = opt.amg_coarsening;
     amg_coarse.setup(A0, 1, /*max_coarse=*/1, 0.25, 4, 25, /*on_device=*/false);
     setup_mark("AMG #1 (global N=1 matrix)");
 
@@ -426,6 +427,7 @@ void Subdomain<DType>::build_multi_rank(std::map<int, std::unique_ptr<Domain<DTy
     {
         assemble_low_order_fem();
         setup_mark("low-order FEM assembly");
+        amg_fem.coarsening = opt.amg_coarsening;
         amg_fem.setup(A_fem_hst, cheby_order);
         setup_mark("AMG #2 (hierarchy, upload, collapsed coarse levels)");
     }

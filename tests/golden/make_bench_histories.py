@@ -36,7 +36,7 @@ CASES = {
 
 
 def key_of(rec):
-    return (tuple(rec["nel"]), rec["N"], rec["r"], rec["eps"], rec["ranks"], rec["tolerance"], rec.get("coarsening", "pmis"))
+    return (tuple(rec["nel"]), rec["N"], rec["r"], rec["eps"], rec["ranks"], rec["tolerance"], rec.get("coarsening", "hmis"))
 
 
 def run(name, coarsening):
@@ -63,7 +63,7 @@ def run(name, coarsening):
 
 def main():
     names = [a for a in sys.argv[1:] if not a.startswith("--")]
-    coarsening = "pmis"
+    coarsening = "hmis"
     for a in sys.argv[1:]:
         if a.startswith("--coarsening="):
             coarsening = a.split("=")[1]

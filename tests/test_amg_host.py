@@ -8,13 +8,13 @@ import scipy.sparse as sp
 from oracle import amg as oamg
 
 
-def product_hierarchy(prfdd, A, cheby_order=2, max_coarse=9):
+def product_hierarchy(prfdd, A, cheby_order=2, max_coarse=9, coarsening=-1):
     L = prfdd.lib()
     A = A.tocsr(); A.sort_indices()
     ptr, col, val = A.indptr.astype(np.int32), A.indices.astype(np.int32), np.ascontiguousarray(A.data, dtype=np.float64)
     h = C.c_void_p()
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    assert L.prfdd_amg_host_setup(C.byref(h), C.c_int(A.shape[0]), vp(ptr), vp(col), vp(val), C.c_int(cheby_order), C.c_int(max_coarse)) == 0
+    assert L.prfdd_amg_host_setup_ex(C.byref(h), C.c_int(A.shape[0]), vp(ptr), vp(col), vp(val), C.c_int(cheby_order), C.c_int(max_coarse), C.c_int(coarsening)) == 0
     out = []
     for l in range(L.prfdd_amg_host_num_levels(h)):
         sz = (C.c_int * 4)()
@@ -54,9 +54,14 @@ def random_spd(n, seed):
 
 @pytest.mark.parametrize("name,A", [("lap3d_12", laplace3d(12)), ("lap3d_aniso", laplace3d(9, 0.01)), ("rand_spd", random_spd(1500, 3))])
 @pytest.mark.parametrize("order", [1, 2, 3])
-def test_hierarchy_matches_oracle(prfdd, name, A, order):
-    Ho = oamg.Hierarchy(A, cheby_order=order)
-    Hp, Ainv = product_hierarchy(prfdd, A, order)
+@pytest.mark.parametrize("coarsening", ["pmis", "hmis"])
+def test_hierarchy_matches_oracle(prfdd, name, A, order, coarsening):
+    oamg.set_coarsening(coarsening)
+    try:
+        Ho = oamg.Hierarchy(A, cheby_order=order)
+    finally:
+        oamg.set_coarsening("hmis")
+    Hp, Ainv = product_hierarchy(prfdd, A, order, coarsening=0 if coarsening == "pmis" else 1)
     assert len(Hp) == Ho.num_levels
     for lo, lp in zip(Ho.levels, Hp):
         assert lo.n == lp["n"]
@@ -70,6 +75,22 @@ def test_hierarchy_matches_oracle(prfdd, name, A, order):
             assert abs(lo.P - lp["P"]).max() <= 1e-12
             assert np.asarray(lp["P"].getnnz(axis=1)).max() <= 4
     assert np.abs(Ainv - Ho.levels[-1].Ainv).max() <= 1e-9 * np.abs(Ainv).max()
+
+
+def test_hmis_is_a_valid_first_pass_colouring():
+    """properties of the Ruge-Stueben first pass (HMIS on one process): every F point with strong connections depends strongly on
+    at least one C point; no two C points ... are NOT forbidden to be strongly connected in general, but on the 7-point Laplacian
+    the pass yields the red-black colouring (half the points, no C-C connection)"""
+    A = laplace3d(10)
+    S = oamg.strength(A)
+    cf = oamg.rs_first_pass(S)
+    n = A.shape[0]
+    assert set(np.unique(cf)) == {-1, 1}
+    isC = cf == 1
+    dep_on_C = np.asarray((S.astype(np.float64) @ isC.astype(np.float64))).ravel()
+    assert np.all(dep_on_C[~isC] >= 1)
+    Sc = S[isC][:, isC]
+    assert Sc.nnz == 0 and abs(isC.sum() - n / 2) <= 1
 
 
 def test_vcycle_contracts():
