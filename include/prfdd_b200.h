@@ -50,6 +50,12 @@ long long prfdd_launch_count(void);
 void prfdd_launch_count_reset(void);
 /* kernels replayed from a captured CUDA graph are counted through this */
 void prfdd_launch_count_add(long long n);
+/* ALGORITHMIC bytes of the kernels launched since the last reset: every launcher adds what its kernel must move at least
+ * (each operand once: SURVEY 8d; e.g. 64 B/point for the SEM operator, 12*nnz + 4*(rows+1) + 8*cols + epilogue operands for an
+ * SpMV).  bench.py divides the sum over a solve by the solve time for its whole-solve roofline fraction. */
+double prfdd_algorithmic_bytes(void);
+void prfdd_algorithmic_bytes_reset(void);
+void prfdd_algorithmic_bytes_add(double bytes);
 
 /* replaces occa::memory malloc / free / copyFrom / copyTo / device.finish */
 int prfdd_malloc(void **dptr, size_t bytes);
@@ -70,6 +76,13 @@ int prfdd_reduce_ws_destroy(prfdd_reduce_ws *ws);
  * domain.tpp:602-609).  D_hat is row-major n*n, D_hat[i*n+m] = dl_m/dxi(xi_i) (domain.tpp:312). */
 int prfdd_stiffness_matrix(double *Au, const double *u, const double *D_hat, const double *const g[6],
                            int num_elements, int n, int dim, prfdd_stream_t stream);
+/* the same with a HOST copy of D_hat (same n*n values).  The fastest 3D kernels (n <= 10) take D as a kernel parameter, i.e. from
+ * the constant bank, which can only be filled from host memory; without the host copy (the form above) the generic kernel that
+ * reads D from device memory runs instead.  Nothing is cached by address and no entry point synchronises, so both forms are
+ * safe under stream capture and with reused allocations.  The bulk-async variant (n = 6, 8) additionally needs u and g[0..5]
+ * 16-byte aligned; otherwise the register-staged kernel runs. */
+int prfdd_stiffness_matrix_hd(double *Au, const double *u, const double *D_hat, const double *D_hat_host, const double *const g[6],
+                              int num_elements, int n, int dim, prfdd_stream_t stream);
 
 /* variable-degree composite operator: the region is a sequence of `num_buckets` contiguous runs of
  * equal-degree elements (run b: first point first_point[b], num_elements[b], n[b] points per
@@ -79,6 +92,10 @@ int prfdd_stiffness_matrix(double *Au, const double *u, const double *D_hat, con
 int prfdd_stiffness_matrix_region(double *Au, const double *u, const double *const g[6], int num_buckets,
                                   const int *first_point, const int *num_elements, const int *n,
                                   const double *const *D_hat, int dim, prfdd_stream_t stream);
+/* D_hat_host[b]: host copy of D_hat[b] (see prfdd_stiffness_matrix_hd); NULL = none */
+int prfdd_stiffness_matrix_region_hd(double *Au, const double *u, const double *const g[6], int num_buckets,
+                                     const int *first_point, const int *num_elements, const int *n,
+                                     const double *const *D_hat, const double *const *D_hat_host, int dim, prfdd_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * gather-scatter (direct stiffness summation), index-map form of Q / Q^T
@@ -122,6 +139,7 @@ typedef struct prfdd_csr_matrix
     const int *col;
     const double *val;
     int num_rows;
+    int num_cols;   /* 0: unknown (only used for the algorithmic byte count) */
     int num_nnz;
     int threads_per_row;
     const int *long_rows;

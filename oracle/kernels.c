@@ -33,9 +33,11 @@
  * OCCA's OpenMP backend does with them (config.hpp:34-36).  Every loop trip owns its outputs and the block reductions stay serial
  * inside a block, so the results are bit-identical to the serial build (tests/test_oracle_pin.py checks both). */
 #ifdef ORACLE_OMP
-#define OMP_FOR _Pragma("omp parallel for schedule(static)")
+#define OMP_STR(x) #x
+#define OMP_PRAGMA(x) _Pragma(OMP_STR(x))
+#define OMP_FOR_N(n) OMP_PRAGMA(omp parallel for schedule(static) if ((n) > 8192))   /* small loops (coarse AMG levels) stay serial */
 #else
-#define OMP_FOR
+#define OMP_FOR_N(n)
 #endif
 
 #define BLOCK_SIZE 128
@@ -46,7 +48,7 @@ typedef double EType;
 
 void o_stiffness_matrix_1(DType **GDu, const DType *u, const DType *D_hat, const DType **G, const int num_points, const int poly_degree, const int dim)
 {
-    OMP_FOR
+    OMP_FOR_N(num_points)
     for (int idx = 0; idx < num_points; idx++)
     {
         int n_x = poly_degree + 1;
@@ -99,7 +101,7 @@ void o_stiffness_matrix_1(DType **GDu, const DType *u, const DType *D_hat, const
 
 void o_stiffness_matrix_2(DType *Au, const DType **GDu, const DType *D_hat, const int num_points, const int poly_degree, const int dim)
 {
-    OMP_FOR
+    OMP_FOR_N(num_points)
     for (int idx = 0; idx < num_points; idx++)
     {
         int n_x = poly_degree + 1;
@@ -149,7 +151,7 @@ void o_stiffness_matrix_2(DType *Au, const DType **GDu, const DType *D_hat, cons
 
 void o_initialize_arrays(DType *u_k, DType *r_k, const DType *f, const int num_points)
 {
-    OMP_FOR
+    OMP_FOR_N(num_points)
     for (int idx = 0; idx < num_points; idx++)
     {
         u_k[idx] = 0.0;
@@ -168,7 +170,7 @@ static DType block_tree(DType *s)
 
 void o_residual_norm(DType *block, const DType *r_k, const DType *QQt_r_k, const DType *dirichlet_mask, const int num_points, const int num_blocks)
 {
-    OMP_FOR
+    OMP_FOR_N(num_blocks)
     for (int group = 0; group < num_blocks; ++group)
     {
         DType r_norm[BLOCK_SIZE];
@@ -186,7 +188,7 @@ void o_residual_norm(DType *block, const DType *r_k, const DType *QQt_r_k, const
 
 void o_projection_inner_products(DType *block, const DType *z_k, const DType *r_k, const DType *p_k, const DType *q_k, const int num_points, const int num_blocks)
 {
-    OMP_FOR
+    OMP_FOR_N(num_blocks)
     for (int group = 0; group < num_blocks; ++group)
     {
         DType gamma_sum[BLOCK_SIZE];
@@ -212,7 +214,7 @@ void o_projection_inner_products(DType *block, const DType *z_k, const DType *r_
 
 void o_solution_and_residual_update(DType *u_k, DType *r_kp1, const DType *r_k, const DType *p_k, const DType *q_k, DType alpha_k, const int num_points)
 {
-    OMP_FOR
+    OMP_FOR_N(num_points)
     for (int idx = 0; idx < num_points; idx++)
     {
         u_k[idx] += alpha_k * p_k[idx];
@@ -222,7 +224,7 @@ void o_solution_and_residual_update(DType *u_k, DType *r_kp1, const DType *r_k, 
 
 void o_inner_product_flexible(DType *block, const DType *r_k, const DType *r_kp1, const DType *z_k, const int num_points, const int num_blocks)
 {
-    OMP_FOR
+    OMP_FOR_N(num_blocks)
     for (int group = 0; group < num_blocks; ++group)
     {
         DType theta_sum[BLOCK_SIZE];
@@ -240,7 +242,7 @@ void o_inner_product_flexible(DType *block, const DType *r_k, const DType *r_kp1
 
 void o_residual_and_search_update(DType *p_k, DType *r_k, const DType *z_k, const DType *r_kp1, DType beta_k, const int num_points)
 {
-    OMP_FOR
+    OMP_FOR_N(num_points)
     for (int idx = 0; idx < num_points; idx++)
     {
         p_k[idx] = z_k[idx] + beta_k * p_k[idx];
@@ -250,7 +252,7 @@ void o_residual_and_search_update(DType *p_k, DType *r_k, const DType *z_k, cons
 
 void o_inner_product_mask(DType *block, const DType *u_k, const DType *v_k, const DType *dirichlet_mask, const int num_points, const int num_blocks)
 {
-    OMP_FOR
+    OMP_FOR_N(num_blocks)
     for (int group = 0; group < num_blocks; ++group)
     {
         DType sum[BLOCK_SIZE];
@@ -270,7 +272,7 @@ void o_inner_product_mask(DType *block, const DType *u_k, const DType *v_k, cons
 
 void o_sub_stiffness_matrix_1(DType **GDu, const DType *u, const DType **D_hat_ptr, const int *offset, const int *vert, const int *level, const DType **G, const int num_points, const DType *poly_degree, const int dim)
 {
-    OMP_FOR
+    OMP_FOR_N(num_points)
     for (int idx = 0; idx < num_points; idx++)
     {
         int o = offset[idx];
@@ -323,7 +325,7 @@ void o_sub_stiffness_matrix_1(DType **GDu, const DType *u, const DType **D_hat_p
 
 void o_sub_stiffness_matrix_2(DType *Au, const DType **GDu, const DType **D_hat_ptr, const int *offset, const int *vert, const int *level, const int num_points, const DType *poly_degree, const int dim)
 {
-    OMP_FOR
+    OMP_FOR_N(num_points)
     for (int idx = 0; idx < num_points; idx++)
     {
         int o = offset[idx];
@@ -373,7 +375,7 @@ void o_sub_stiffness_matrix_2(DType *Au, const DType **GDu, const DType **D_hat_
 
 void o_sub_inner_product(DType *block, const DType *u, const DType *v, const int num_values, const int num_blocks)
 {
-    OMP_FOR
+    OMP_FOR_N(num_blocks)
     for (int group = 0; group < num_blocks; ++group)
     {
         DType uv[BLOCK_SIZE];
@@ -391,7 +393,7 @@ void o_sub_inner_product(DType *block, const DType *u, const DType *v, const int
 
 void o_sub_weighted_inner_product(DType *block, const DType *u, const DType *v, const DType *w, const int num_values, const int num_blocks)
 {
-    OMP_FOR
+    OMP_FOR_N(num_blocks)
     for (int group = 0; group < num_blocks; ++group)
     {
         DType uv[BLOCK_SIZE];
@@ -409,7 +411,7 @@ void o_sub_weighted_inner_product(DType *block, const DType *u, const DType *v, 
 
 void o_sub_projection_inner_products(DType *block, const DType *z_k, const DType *r_k, const DType *p_k, const DType *q_k, const DType *weight, const int num_values, const int num_blocks)
 {
-    OMP_FOR
+    OMP_FOR_N(num_blocks)
     for (int group = 0; group < num_blocks; ++group)
     {
         DType gamma_sum[BLOCK_SIZE];
@@ -435,7 +437,7 @@ void o_sub_projection_inner_products(DType *block, const DType *z_k, const DType
 
 void o_sub_search_update_inner_product(DType *block, const DType *r_k, const DType *r_kp1, const DType *z_k, const DType *weight, const int num_points, const int num_blocks)
 {
-    OMP_FOR
+    OMP_FOR_N(num_blocks)
     for (int group = 0; group < num_blocks; ++group)
     {
         DType theta_sum[BLOCK_SIZE];
@@ -453,19 +455,19 @@ void o_sub_search_update_inner_product(DType *block, const DType *r_k, const DTy
 
 void o_copy_from_domain_data(DType *u, const EType *v, const int num_points)
 {
-    OMP_FOR
+    OMP_FOR_N(num_points)
     for (int idx = 0; idx < num_points; idx++) u[idx] = (DType)(v[idx]);
 }
 
 void o_copy_to_domain_data(EType *u, const DType *v, const int num_points)
 {
-    OMP_FOR
+    OMP_FOR_N(num_points)
     for (int idx = 0; idx < num_points; idx++) u[idx] = (EType)(v[idx]);
 }
 
 void o_restriction_1(DType *Ju, const DType *J_cf, const DType *u, const int num_points, const int n_f, const int n_c, const int dim)
 {
-    OMP_FOR
+    OMP_FOR_N(num_points)
     for (int idx = 0; idx < num_points; idx++)
     {
         int num_elem_points_fine = (dim == 2) ? n_f * n_f : n_f * n_f * n_f;
@@ -500,7 +502,7 @@ void o_restriction_1(DType *Ju, const DType *J_cf, const DType *u, const int num
 
 void o_restriction_2(DType *Ju, const DType *J_cf, const DType *u, const int num_points, const int n_f, const int n_c, const int dim)
 {
-    OMP_FOR
+    OMP_FOR_N(num_points)
     for (int idx = 0; idx < num_points; idx++)
     {
         int num_elem_points_fine = (dim == 2) ? n_f * n_c : n_f * n_f * n_c;
@@ -535,7 +537,7 @@ void o_restriction_2(DType *Ju, const DType *J_cf, const DType *u, const int num
 
 void o_restriction_3(DType *Ju, const DType *J_cf, const DType *u, const int num_points, const int n_f, const int n_c)
 {
-    OMP_FOR
+    OMP_FOR_N(num_points)
     for (int idx = 0; idx < num_points; idx++)
     {
         int num_elem_points_fine = n_f * n_c * n_c;
@@ -560,7 +562,7 @@ void o_restriction_3(DType *Ju, const DType *J_cf, const DType *u, const int num
 
 void o_csr_multiply(DType *Au, const int *A_ptr, const int *A_col, const DType *A_val, const DType *u, int n)
 {
-    OMP_FOR
+    OMP_FOR_N(n)
     for (int i = 0; i < n; i++)
     {
         DType Au_i = 0.0;
@@ -571,7 +573,7 @@ void o_csr_multiply(DType *Au, const int *A_ptr, const int *A_col, const DType *
 
 void o_csr_multiply_range(DType *Au, const int *A_ptr, const int *A_col, const DType *A_val, const DType *u, int row_start, int row_end)
 {
-    OMP_FOR
+    OMP_FOR_N(row_end)
     for (int i = row_start; i <= row_end; i++)
     {
         DType Au_i = 0.0;
@@ -582,7 +584,7 @@ void o_csr_multiply_range(DType *Au, const int *A_ptr, const int *A_col, const D
 
 void o_csr_multiply_weight(DType *Au, const int *A_ptr, const int *A_col, const DType *A_val, const DType *u, const DType *weight, int n)
 {
-    OMP_FOR
+    OMP_FOR_N(n)
     for (int i = 0; i < n; i++)
     {
         DType Au_i = 0.0;
@@ -595,25 +597,25 @@ void o_csr_multiply_weight(DType *Au, const int *A_ptr, const int *A_col, const 
 
 void o_set_to_value(DType *u, DType alpha, int n, int offset)
 {
-    OMP_FOR
+    OMP_FOR_N(n)
     for (int i = 0; i < n; i++) u[i + offset] = alpha;
 }
 
 void o_invert_vector_elements(DType *u, int n)
 {
-    OMP_FOR
+    OMP_FOR_N(n)
     for (int i = 0; i < n; i++) u[i] = 1.0 / u[i];
 }
 
 void o_vector_vector_addition(DType *uv, const DType alpha, const DType *u, const DType beta, const DType *v, const int n)
 {
-    OMP_FOR
+    OMP_FOR_N(n)
     for (int i = 0; i < n; i++) uv[i] = alpha * u[i] + beta * v[i];
 }
 
 void o_vector_scaling(DType *au, const DType alpha, const DType *u, const int n)
 {
-    OMP_FOR
+    OMP_FOR_N(n)
     for (int i = 0; i < n; i++) au[i] = alpha * u[i];
 }
 
@@ -622,7 +624,7 @@ void o_vector_scaling(DType *au, const DType alpha, const DType *u, const int n)
 /* y = alpha*A*x + beta*y   (AMG/csr_matrix.cpp:114-125) */
 void o_amg_matvec(DType *y, const int *ptr, const int *col, const DType *val, const DType *x, DType alpha, DType beta, int num_rows)
 {
-    OMP_FOR
+    OMP_FOR_N(num_rows)
     for (int row = 0; row < num_rows; row++)
     {
         DType Ax = 0.0;
@@ -634,7 +636,7 @@ void o_amg_matvec(DType *y, const int *ptr, const int *col, const DType *val, co
 /* Sr = S*(f - A u); w = alpha*Sr   (subdomain.tpp:21-33) */
 void o_scaled_residual(DType *Sr, DType *w, const int *ptr, const int *col, const DType *val, const DType *u, const DType *f, const DType *S, DType alpha, int num_rows)
 {
-    OMP_FOR
+    OMP_FOR_N(num_rows)
     for (int row = 0; row < num_rows; row++)
     {
         DType Ax = 0.0;
@@ -647,21 +649,21 @@ void o_scaled_residual(DType *Sr, DType *w, const int *ptr, const int *col, cons
 /* v = D*(A*(D*w)); w = alpha*r + v   (subdomain.tpp:47-61) */
 void o_polynomial_evaluation(DType *w, DType *v, const int *ptr, const int *col, const DType *val, const DType *r, const DType *D_val, DType alpha, int num_rows)
 {
-    OMP_FOR
+    OMP_FOR_N(num_rows)
     for (int row = 0; row < num_rows; row++)
     {
         DType tmp = 0.0;
         for (int idx = ptr[row]; idx < ptr[row + 1]; idx++) tmp += val[idx] * D_val[col[idx]] * w[col[idx]];
         v[row] = D_val[row] * tmp;
     }
-    OMP_FOR
+    OMP_FOR_N(num_rows)
     for (int row = 0; row < num_rows; row++) w[row] = alpha * r[row] + v[row];
 }
 
 /* u += D*w   (subdomain.tpp:74-78) */
 void o_update_field(DType *u, const DType *w, const DType *D_val, int size)
 {
-    OMP_FOR
+    OMP_FOR_N(size)
     for (int idx = 0; idx < size; idx++) u[idx] += D_val[idx] * w[idx];
 }
 
@@ -669,13 +671,13 @@ void o_update_field(DType *u, const DType *w, const DType *D_val, int size)
 
 void o_vector_set_to_value(DType *data, const DType value, const int size)
 {
-    OMP_FOR
+    OMP_FOR_N(size)
     for (int idx = 0; idx < size; idx++) data[idx] = value;
 }
 
 void o_main_scaled_residual(DType *Sr, DType *w, const DType *f_m_Au, const DType *S, const DType alpha, const int size)
 {
-    OMP_FOR
+    OMP_FOR_N(size)
     for (int idx = 0; idx < size; idx++)
     {
         Sr[idx] = S[idx] * f_m_Au[idx];
@@ -685,7 +687,7 @@ void o_main_scaled_residual(DType *Sr, DType *w, const DType *f_m_Au, const DTyp
 
 void o_main_polynomial_evaluation(DType *w, DType *v, const DType *r, const DType *D_val, const DType alpha, const int size)
 {
-    OMP_FOR
+    OMP_FOR_N(size)
     for (int idx = 0; idx < size; idx++)
     {
         v[idx] *= D_val[idx];
@@ -695,13 +697,13 @@ void o_main_polynomial_evaluation(DType *w, DType *v, const DType *r, const DTyp
 
 void o_main_update_field(DType *u, const DType *w, const DType *D_val, const int size)
 {
-    OMP_FOR
+    OMP_FOR_N(size)
     for (int idx = 0; idx < size; idx++) u[idx] += D_val[idx] * w[idx];
 }
 
 void o_vector_multiplication(DType *uv, const DType *u, const DType *v, const int size)
 {
-    OMP_FOR
+    OMP_FOR_N(size)
     for (int idx = 0; idx < size; idx++) uv[idx] = u[idx] * v[idx];
 }
 

@@ -8,13 +8,16 @@
 namespace prfdd
 {
 extern long long g_launch_count;
+extern double g_algorithmic_bytes;
 
 inline cudaStream_t S(prfdd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// every launcher ends with this: counts the launch, reports launch-configuration errors
-inline int launched()
+// every launcher ends with this: counts the launch and the ALGORITHMIC bytes of the kernel (what it must move at least: every
+// operand once), reports launch-configuration errors.  The byte count feeds bench.py's whole-solve roofline figure.
+inline int launched(double algorithmic_bytes = 0.0)
 {
     ++g_launch_count;
+    g_algorithmic_bytes += algorithmic_bytes;
     return (int)cudaGetLastError();
 }
 

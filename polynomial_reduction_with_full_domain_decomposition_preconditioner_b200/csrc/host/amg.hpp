@@ -678,6 +678,7 @@ struct DeviceCSR
         desc = prfdd_csr_matrix();
         desc.ptr = ptr.as<int>(); desc.col = col.as<int>(); desc.val = val.as<double>();
         desc.num_rows = num_rows;
+        desc.num_cols = num_cols;
         long_rows = ::plan_csr(desc, A.ptr.data());
         tpr = desc.threads_per_row;
     }

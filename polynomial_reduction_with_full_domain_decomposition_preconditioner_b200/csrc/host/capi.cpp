@@ -23,6 +23,7 @@ struct prfdd_solver
     std::unique_ptr<Subdomain<PTYPE>> subdomain;
     Domain<STYPE> *domain = nullptr;
     dev::memory u_star, f, u;
+    dev::memory apply_in, apply_out; // persistent operands of prfdd_solver_apply: a stable key for the preconditioner's graph cache
     double *pin_in = nullptr, *pin_out = nullptr;
     Comm comm;
     Timer<double> tmr;
@@ -302,7 +303,12 @@ int prfdd_solver_apply(prfdd_solver *s, int what, const double *in_host, double 
         const int P = d->num_local_points;
         if (what == PRFDD_APPLY_STIFFNESS || what == PRFDD_APPLY_DSSUM || what == PRFDD_APPLY_DSSUM_WEIGHTED || what == PRFDD_APPLY_PRECONDITIONER)
         {
-            dev::memory a = device.malloc<double>(P), b = device.malloc<double>(P);
+            if (!s->apply_in.is_initialized())
+            {
+                s->apply_in = device.malloc<double>(P);
+                s->apply_out = device.malloc<double>(P);
+            }
+            dev::memory &a = s->apply_in, &b = s->apply_out;
             a.copyFrom(in_host, sizeof(double) * P);
             if (what == PRFDD_APPLY_STIFFNESS) d->stiffness_matrix(b, a);
             else if (what == PRFDD_APPLY_DSSUM) d->direct_stiffness_summation(b, a, true, false);

@@ -157,6 +157,7 @@ class CSR_Matrix
         desc = prfdd_csr_matrix();
         desc.ptr = ptr.as<int>(); desc.col = col.as<int>(); desc.val = (const double *)val.ptr();
         desc.num_rows = num_rows;
+        desc.num_cols = num_cols;
         long_rows = plan_csr(desc, ptr_hst.data());
         threads_per_row = desc.threads_per_row;
         static const bool no_unit = getenv("PRFDD_CSR_NO_UNIT") != nullptr;

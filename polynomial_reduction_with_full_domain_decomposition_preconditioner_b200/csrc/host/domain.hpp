@@ -472,6 +472,7 @@ void Domain<DType>::direct_stiffness_summation(const memory &QQtu, const memory 
 {
     // domain.tpp:582-600
     dev::check_rc(prfdd_gather(dp(work_dev[0]), Qt.ptr.template as<int>(), Qt.col.template as<int>(), dp(u), apply_assembled_weight ? dp(assembled_weight) : nullptr, num_local_nodes, st()), "dssum/gather");
+    prfdd_algorithmic_bytes_add(12.0 * num_local_points + 8.0 * num_local_nodes); // gathered points (index + value) and the node vector the scatter reads
     halo_exchange(work_dev[0]);
     dev::check_rc(prfdd_scatter(dp(QQtu), Q.col.template as<int>(), dp(work_dev[0]), apply_dirichlet_mask ? dp(dirichlet_mask) : nullptr, num_local_points, st()), "dssum/scatter");
 }
@@ -482,7 +483,7 @@ void Domain<DType>::stiffness_matrix(const memory &Au, const memory &u, bool app
     // domain.tpp:602-609
     const double *g[6];
     for (int c = 0; c < 6; c++) g[c] = dp(geom_fact[c]);
-    dev::check_rc(prfdd_stiffness_matrix(dp(Au), dp(u), dp(D_hat), g, num_local_elements, poly_degree + 1, prfdd_host::dim, st()), "Domain::stiffness_matrix");
+    dev::check_rc(prfdd_stiffness_matrix_hd(dp(Au), dp(u), dp(D_hat), D_hat_hst.data(), g, num_local_elements, poly_degree + 1, prfdd_host::dim, st()), "Domain::stiffness_matrix");
     if (apply_dssum) direct_stiffness_summation(Au, Au, true, false);
 }
 

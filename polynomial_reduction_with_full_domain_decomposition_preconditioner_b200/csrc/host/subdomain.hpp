@@ -63,7 +63,7 @@ struct Stiffness_Operator
 
     // runs of equal-degree elements (replace the per-point element/vertex/level/offset arrays, tpp:1603-1630)
     std::vector<int> bucket_first_point, bucket_num_elements, bucket_n;
-    std::vector<const double *> bucket_D;
+    std::vector<const double *> bucket_D, bucket_D_hst; // device / host copies of the run's derivative matrix
 };
 
 template <typename DType>
@@ -160,6 +160,7 @@ class Subdomain
     struct GraphKey { const void *in; void *out; int type; bool operator<(const GraphKey &o) const { return std::tie(in, out, type) < std::tie(o.in, o.out, o.type); } };
     std::map<GraphKey, cudaGraphExec_t> graphs;
     long long launches_per_apply = 0;
+    double bytes_per_apply = 0.0; // algorithmic bytes of one application (prfdd_algorithmic_bytes)
 
     cudaStream_t st() const { return prfdd_host::device.stream; }
     static double *dp(const memory &m) { return m.as<double>(); }
@@ -437,6 +438,7 @@ void Subdomain<DType>::build_single_rank(std::map<int, std::unique_ptr<Domain<DT
             subdomain_operator.bucket_num_elements.push_back((int)(e2 - e));
             subdomain_operator.bucket_n.push_back(subdomain_region[e].poly_degree + 1);
             subdomain_operator.bucket_D.push_back(dp(D_hat[level_degree[subdomain_region[e].poly_degree]].second));
+            subdomain_operator.bucket_D_hst.push_back(D_hat[level_degree[subdomain_region[e].poly_degree]].first.data());
             e = e2;
         }
     }
@@ -882,8 +884,9 @@ void Subdomain<DType>::stiffness_matrix(const memory &Au, const memory &u)
     }
     const double *g[6];
     for (int c = 0; c < 6; c++) g[c] = dp(subdomain_operator.geom_fact[c]);
-    dev::check_rc(prfdd_stiffness_matrix_region(dp(Au), dp(u), g, (int)subdomain_operator.bucket_n.size(), subdomain_operator.bucket_first_point.data(),
-                                                subdomain_operator.bucket_num_elements.data(), subdomain_operator.bucket_n.data(), subdomain_operator.bucket_D.data(), prfdd_host::dim, st()),
+    dev::check_rc(prfdd_stiffness_matrix_region_hd(dp(Au), dp(u), g, (int)subdomain_operator.bucket_n.size(), subdomain_operator.bucket_first_point.data(),
+                                                   subdomain_operator.bucket_num_elements.data(), subdomain_operator.bucket_n.data(), subdomain_operator.bucket_D.data(),
+                                                   subdomain_operator.bucket_D_hst.data(), prfdd_host::dim, st()),
                   "Subdomain::stiffness_matrix");
 }
 
@@ -1153,8 +1156,10 @@ void Subdomain<DType>::run_captured(int type, const memory &u_l, const memory &f
     if (!opt.use_cuda_graph || timer.enabled)
     {
         long long before = prfdd_launch_count();
+        const double bytes_before = prfdd_algorithmic_bytes();
         body();
         launches_per_apply = prfdd_launch_count() - before;
+        bytes_per_apply = prfdd_algorithmic_bytes() - bytes_before;
         return;
     }
     GraphKey key{f_l.ptr(), u_l.ptr(), type};
@@ -1166,10 +1171,14 @@ void Subdomain<DType>::run_captured(int type, const memory &u_l, const memory &f
         dev::check(cudaStreamSynchronize(st()), "graph warm-up");
         cudaGraph_t graph;
         long long before = prfdd_launch_count();
+        const double bytes_before = prfdd_algorithmic_bytes();
         dev::check(cudaStreamBeginCapture(st(), cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
         body();
         dev::check(cudaStreamEndCapture(st(), &graph), "cudaStreamEndCapture");
         launches_per_apply = prfdd_launch_count() - before;
+        bytes_per_apply = prfdd_algorithmic_bytes() - bytes_before;
+        prfdd_launch_count_add(-launches_per_apply); // the captured run launched nothing; the warm-up run above did the work
+        prfdd_algorithmic_bytes_add(-bytes_per_apply);
         cudaGraphExec_t exec;
         dev::check(cudaGraphInstantiate(&exec, graph, 0), "cudaGraphInstantiate");
         cudaGraphDestroy(graph);
@@ -1180,6 +1189,7 @@ void Subdomain<DType>::run_captured(int type, const memory &u_l, const memory &f
     dev::check(cudaGraphLaunch(it->second, st()), "cudaGraphLaunch");
     // the kernels inside the graph are this library's launches too
     prfdd_launch_count_add(launches_per_apply);
+    prfdd_algorithmic_bytes_add(bytes_per_apply);
 }
 
 template <typename DType>

@@ -349,6 +349,7 @@ void Subdomain<DType>::build_multi_rank(std::map<int, std::unique_ptr<Domain<DTy
             subdomain_operator.bucket_num_elements.push_back((int)(e2 - e));
             subdomain_operator.bucket_n.push_back(subdomain_region[e].poly_degree + 1);
             subdomain_operator.bucket_D.push_back(dp(D_hat[level_degree[subdomain_region[e].poly_degree]].second));
+            subdomain_operator.bucket_D_hst.push_back(D_hat[level_degree[subdomain_region[e].poly_degree]].first.data());
             e = e2;
         }
     }

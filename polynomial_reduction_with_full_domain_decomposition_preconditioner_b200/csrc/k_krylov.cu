@@ -176,13 +176,13 @@ int prfdd_axpy_dev(double *y, const double *a, double sign, const double *x, int
 {
     if (n <= 0) return 0;
     k_axpy_dev<<<stream_grid(n, 256, 2, 8), 256, 0, S(stream)>>>(y, a, sign, x, n);
-    return launched();
+    return launched(24.0 * n);
 }
 int prfdd_residual_and_search_update_gated(double *p_k, double *r_k, const double *z_k, const double *r_kp1, const double *beta, const int *skip_flag, int n, prfdd_stream_t stream)
 {
     if (n <= 0) return 0;
     k_search_update_gated<<<stream_grid(n, 256, 2, 8), 256, 0, S(stream)>>>(p_k, r_k, z_k, r_kp1, beta, skip_flag, n);
-    return launched();
+    return launched(40.0 * n);
 }
 
 } // extern "C"

@@ -358,6 +358,12 @@ template <int N>
 static int launch_ax3d(double *Au, const double *u, const G6 &G, const double *D_host, const double *D_dev, long long first_point, int num_elems, cudaStream_t st)
 {
     if (num_elems <= 0) return 0;
+    if (N <= 10 && !D_host)
+    {
+        // no host copy of D to put into the constant bank: the generic kernel reads D from device memory
+        k_ax3d_big<N><<<num_elems, N * N, 0, st>>>(Au, u, G, D_dev, first_point, num_elems);
+        return launched(64.0 * num_elems * N * N * N);
+    }
     if constexpr (N <= 10)
     {
         constexpr int EPB = epb3d<N>();
@@ -367,11 +373,13 @@ static int launch_ax3d(double *Au, const double *u, const G6 &G, const double *D
         {
             // bulk-async variant: needs 16-byte aligned element blocks (static shared memory: n <= 8)
             static const bool no_bulk = getenv("PRFDD_AX_NO_BULK") != nullptr;
-            if (!no_bulk && first_point % 2 == 0)
+            uintptr_t align = reinterpret_cast<uintptr_t>(u);
+            for (int c = 0; c < 6; c++) align |= reinterpret_cast<uintptr_t>(G.g[c]);
+            if (!no_bulk && first_point % 2 == 0 && align % 16 == 0)
             {
                 constexpr int MINB = (N == 6) ? 10 : 6;
                 k_ax3d_bulk<N, MINB><<<num_elems, N * N, 0, st>>>(Au, u, G, Dc, D_dev, first_point, num_elems);
-                return launched();
+                return launched(64.0 * num_elems * N * N * N);
             }
         }
         int grid = (num_elems + EPB - 1) / EPB;
@@ -381,7 +389,7 @@ static int launch_ax3d(double *Au, const double *u, const G6 &G, const double *D
     {
         k_ax3d_big<N><<<num_elems, N * N, 0, st>>>(Au, u, G, D_dev, first_point, num_elems);
     }
-    return launched();
+    return launched(64.0 * num_elems * N * N * N); // u 8 + six factors 48 + Au 8 per point
 }
 
 template <int N>
@@ -391,34 +399,12 @@ static int launch_ax2d(double *Au, const double *u, const G6 &G, const double *D
     constexpr int EPB = (N * N >= 128) ? 1 : (128 / (N * N));
     int grid = (num_elems + EPB - 1) / EPB;
     k_ax2d<N, EPB><<<grid, N * N * EPB, 0, st>>>(Au, u, G, D_dev, first_point, num_elems);
-    return launched();
+    return launched(40.0 * num_elems * N * N); // u 8 + three factors 24 + Au 8 per point
 }
 
-// host mirror of D (the constant-bank copy for the 3D kernels is filled from host memory)
-struct HostD
-{
-    const double *dev = nullptr;
-    int n = 0;
-    double v[16 * 16];
-};
-static HostD g_hostD[8];
-static int g_hostD_next = 0;
-
-static const double *host_copy_of(const double *D_dev, int n, cudaStream_t st)
-{
-    for (auto &h : g_hostD)
-        if (h.dev == D_dev && h.n == n) return h.v;
-    HostD &h = g_hostD[g_hostD_next];
-    g_hostD_next = (g_hostD_next + 1) % 8;
-    // D matrices are written once at setup; a blocking copy the first time a pointer is seen is fine
-    cudaStreamSynchronize(st);
-    if (cudaMemcpy(h.v, D_dev, sizeof(double) * n * n, cudaMemcpyDeviceToHost) != cudaSuccess) return nullptr;
-    h.dev = D_dev;
-    h.n = n;
-    return h.v;
-}
-
-static int ax_dispatch(double *Au, const double *u, const G6 &G, const double *D_dev, long long first_point, int num_elems, int n, int dim, cudaStream_t st)
+// D_host: host copy of D_dev (same n*n values) or NULL.  The 3D kernels for n <= 10 take D as a kernel parameter (constant bank);
+// without a host copy the generic kernel, which reads D from device memory, is used -- nothing is cached by address.
+static int ax_dispatch(double *Au, const double *u, const G6 &G, const double *D_dev, const double *D_host, long long first_point, int num_elems, int n, int dim, cudaStream_t st)
 {
     if (num_elems <= 0) return 0;
     if (dim == 2)
@@ -431,8 +417,7 @@ static int ax_dispatch(double *Au, const double *u, const G6 &G, const double *D
         default: return -4;
         }
     }
-    const double *Dh = (n <= 10) ? host_copy_of(D_dev, n, st) : nullptr;
-    if (n <= 10 && !Dh) return -5;
+    const double *Dh = D_host;
     switch (n)
     {
 #define C3(N) case N: return launch_ax3d<N>(Au, u, G, Dh, D_dev, first_point, num_elems, st);
@@ -519,23 +504,33 @@ using namespace prfdd;
 
 extern "C" {
 
-int prfdd_stiffness_matrix(double *Au, const double *u, const double *D_hat, const double *const g[6], int num_elements, int n, int dim, prfdd_stream_t stream)
+int prfdd_stiffness_matrix_hd(double *Au, const double *u, const double *D_hat, const double *D_hat_host, const double *const g[6], int num_elements, int n, int dim, prfdd_stream_t stream)
 {
     G6 G;
     for (int c = 0; c < 6; c++) G.g[c] = g[c];
-    return ax_dispatch(Au, u, G, D_hat, 0, num_elements, n, dim, S(stream));
+    return ax_dispatch(Au, u, G, D_hat, D_hat_host, 0, num_elements, n, dim, S(stream));
 }
 
-int prfdd_stiffness_matrix_region(double *Au, const double *u, const double *const g[6], int num_buckets, const int *first_point, const int *num_elements, const int *n, const double *const *D_hat, int dim, prfdd_stream_t stream)
+int prfdd_stiffness_matrix(double *Au, const double *u, const double *D_hat, const double *const g[6], int num_elements, int n, int dim, prfdd_stream_t stream)
+{
+    return prfdd_stiffness_matrix_hd(Au, u, D_hat, nullptr, g, num_elements, n, dim, stream);
+}
+
+int prfdd_stiffness_matrix_region_hd(double *Au, const double *u, const double *const g[6], int num_buckets, const int *first_point, const int *num_elements, const int *n, const double *const *D_hat, const double *const *D_hat_host, int dim, prfdd_stream_t stream)
 {
     G6 G;
     for (int c = 0; c < 6; c++) G.g[c] = g[c];
     for (int b = 0; b < num_buckets; b++)
     {
-        int rc = ax_dispatch(Au, u, G, D_hat[b], first_point[b], num_elements[b], n[b], dim, S(stream));
+        int rc = ax_dispatch(Au, u, G, D_hat[b], D_hat_host ? D_hat_host[b] : nullptr, first_point[b], num_elements[b], n[b], dim, S(stream));
         if (rc) return rc;
     }
     return 0;
+}
+
+int prfdd_stiffness_matrix_region(double *Au, const double *u, const double *const g[6], int num_buckets, const int *first_point, const int *num_elements, const int *n, const double *const *D_hat, int dim, prfdd_stream_t stream)
+{
+    return prfdd_stiffness_matrix_region_hd(Au, u, g, num_buckets, first_point, num_elements, n, D_hat, nullptr, dim, stream);
 }
 
 int prfdd_restriction(double *u_c, const double *J_cf, const double *u_f, int num_elements, int n_f, int n_c, int dim, prfdd_stream_t stream)
@@ -556,7 +551,8 @@ int prfdd_restriction(double *u_c, const double *J_cf, const double *u_f, int nu
         size_t smem = sizeof(double) * ((size_t)n_f * n_c * 2 + (size_t)n_f * n_f);
         k_restrict2d<<<num_elements, 256, smem, S(stream)>>>(u_c, J_cf, u_f, n_f, n_c, num_elements);
     }
-    return launched();
+    const double pf = dim == 3 ? (double)n_f * n_f * n_f : (double)n_f * n_f, pc = dim == 3 ? (double)n_c * n_c * n_c : (double)n_c * n_c;
+    return launched(8.0 * num_elements * (pf + pc));
 }
 
 } // extern "C"

@@ -128,19 +128,27 @@ static void launch_spmv(const prfdd_csr_matrix &A, const double *x, int row_star
 }
 
 // dispatch on the descriptor
+// epi_bytes: algorithmic bytes per row of the epilogue's operands
 template <class Epi>
-static int spmv(const prfdd_csr_matrix &A, const double *x, int row_start, int num_rows, cudaStream_t st, Epi epi)
+static int spmv(const prfdd_csr_matrix &A, const double *x, int row_start, int num_rows, cudaStream_t st, double epi_bytes, Epi epi)
 {
     if (num_rows <= 0) return 0;
     if (!A.col) return -8;
     const bool unit = A.val == nullptr;
+    // algorithmic bytes: col 4 (+ val 8) per entry, ptr 4 per row, the gathered vector once, the epilogue's operands
+    double bytes = epi_bytes * num_rows;
+    if (x)
+    {
+        const double entries = !A.ptr ? (double)num_rows : (num_rows == A.num_rows && A.num_nnz >= 0) ? (double)A.num_nnz : 0.0;
+        bytes += (unit ? 4.0 : 12.0) * entries + (A.ptr ? 4.0 * (num_rows + 1) : 0.0) + 8.0 * (A.num_cols > 0 ? A.num_cols : num_rows);
+    }
     if (!A.ptr)
     {
         // one entry per row
         if (!x) return -8;
         if (unit) k_spmv_single<true><<<stream_grid(num_rows, 256, 2, 8), 256, 0, st>>>(A.col, nullptr, x, row_start, num_rows, epi);
         else k_spmv_single<false><<<stream_grid(num_rows, 256, 2, 8), 256, 0, st>>>(A.col, A.val, x, row_start, num_rows, epi);
-        return launched();
+        return launched(bytes);
     }
     const int tpr = A.threads_per_row > 0 ? A.threads_per_row : 4;
     const bool lr = x && row_start == 0 && tpr < 32 && A.num_long_rows > 0 && A.long_rows;
@@ -170,7 +178,7 @@ static int spmv(const prfdd_csr_matrix &A, const double *x, int row_start, int n
         }
     }
     if (lr) prfdd_launch_count_add(1);
-    return launched();
+    return launched(bytes);
 }
 
 // the pointer-argument entry points (the reference's kernel signatures + one lanes-per-row hint): no long-row list, no staging
@@ -250,35 +258,35 @@ int prfdd_gather(double *nodes, const int *ptr, const int *col, const double *u,
 {
     if (num_nodes <= 0) return 0;
     k_gather<<<stream_grid(num_nodes, 256, 1, 16), 256, 0, S(stream)>>>(nodes, ptr, col, u, weight, num_nodes);
-    return launched();
+    return launched((weight ? 20.0 : 12.0) * num_nodes); // ptr 4 + result 8 (+ weight 8) per node; the 12 bytes per gathered point are not known here (the caller adds them)
 }
 
 int prfdd_scatter(double *out, const int *node_of_point, const double *nodes, const double *mask, int num_points, prfdd_stream_t stream)
 {
     if (num_points <= 0) return 0;
     k_scatter<<<stream_grid(num_points, 256, 2, 8), 256, 0, S(stream)>>>(out, node_of_point, nodes, mask, num_points);
-    return launched();
+    return launched((mask ? 20.0 : 12.0) * num_points); // index 4 + result 8 (+ mask 8) per point; the node vector (8 per node) is not known here
 }
 
 int prfdd_halo_pack(double *buf, const double *nodes, const int *idx, int count, prfdd_stream_t stream)
 {
     if (count <= 0) return 0;
     k_pack<<<stream_grid(count, 256, 1, 8), 256, 0, S(stream)>>>(buf, nodes, idx, count);
-    return launched();
+    return launched(20.0 * count);
 }
 
 int prfdd_halo_unpack_add(double *nodes, const double *buf, const int *idx, int count, prfdd_stream_t stream)
 {
     if (count <= 0) return 0;
     k_unpack_add<<<stream_grid(count, 256, 1, 8), 256, 0, S(stream)>>>(nodes, buf, idx, count);
-    return launched();
+    return launched(28.0 * count);
 }
 
 int prfdd_scatter_assign(double *dst, const double *buf, const int *idx, int count, prfdd_stream_t stream)
 {
     if (count <= 0) return 0;
     k_scatter_assign<<<stream_grid(count, 256, 1, 8), 256, 0, S(stream)>>>(dst, buf, idx, count);
-    return launched();
+    return launched(20.0 * count);
 }
 
 // lanes per row from the average row length (measured on B200, profiles/r1_spmv_tpr.txt and r1_notes.txt)
@@ -322,30 +330,30 @@ int prfdd_csr_plan(prfdd_csr_matrix *A, const int *ptr_host, int *long_rows_host
 // ---- descriptor entry points ----------------------------------------------------------------
 int prfdd_csrm_multiply(double *Au, const prfdd_csr_matrix *A, const double *u, prfdd_stream_t stream)
 {
-    return spmv(*A, u, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) { Au[row] = ax; });
+    return spmv(*A, u, 0, A->num_rows, S(stream), 8.0, [=] __device__(int row, double ax) { Au[row] = ax; });
 }
 
 int prfdd_csrm_multiply_range(double *Au, const prfdd_csr_matrix *A, const double *u, int row_start, int row_end, prfdd_stream_t stream)
 {
     if (row_end < row_start) return -7; // csr_matrix.tpp:319-323
-    return spmv(*A, u, row_start, row_end - row_start + 1, S(stream), [=] __device__(int row, double ax) { Au[row] = ax; });
+    return spmv(*A, u, row_start, row_end - row_start + 1, S(stream), 8.0, [=] __device__(int row, double ax) { Au[row] = ax; });
 }
 
 int prfdd_csrm_multiply_weight(double *Au, const prfdd_csr_matrix *A, const double *u, const double *weight, prfdd_stream_t stream)
 {
-    return spmv(*A, u, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) { Au[row] = ax * weight[row]; });
+    return spmv(*A, u, 0, A->num_rows, S(stream), 16.0, [=] __device__(int row, double ax) { Au[row] = ax * weight[row]; });
 }
 
 int prfdd_csrm_matvec(double *y, const prfdd_csr_matrix *A, const double *x, double alpha, double beta, prfdd_stream_t stream)
 {
     if (beta == 0.0)
-        return spmv(*A, x, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) { y[row] = alpha * ax; });
-    return spmv(*A, x, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) { y[row] = alpha * ax + beta * y[row]; });
+        return spmv(*A, x, 0, A->num_rows, S(stream), 8.0, [=] __device__(int row, double ax) { y[row] = alpha * ax; });
+    return spmv(*A, x, 0, A->num_rows, S(stream), 16.0, [=] __device__(int row, double ax) { y[row] = alpha * ax + beta * y[row]; });
 }
 
 int prfdd_csrm_residual(double *v, const prfdd_csr_matrix *A, const double *u, const double *f, prfdd_stream_t stream)
 {
-    return spmv(*A, u, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) { v[row] = f[row] - ax; });
+    return spmv(*A, u, 0, A->num_rows, S(stream), 16.0, [=] __device__(int row, double ax) { v[row] = f[row] - ax; });
 }
 
 int prfdd_csrm_cheby_residual(double *r, double *t, const prfdd_csr_matrix *A, const double *u, const double *f, const double *ds, double c_hi, prfdd_stream_t stream)
@@ -353,7 +361,7 @@ int prfdd_csrm_cheby_residual(double *r, double *t, const prfdd_csr_matrix *A, c
     // u == NULL: u = 0, the product A u is skipped (x == nullptr in k_spmv) and the launch shape is irrelevant
     prfdd_csr_matrix B = *A;
     if (!u) B.threads_per_row = 1;
-    return spmv(B, u, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) {
+    return spmv(B, u, 0, A->num_rows, S(stream), 32.0, [=] __device__(int row, double ax) {
         const double d = ds[row];
         const double rr = d * (f[row] - ax);
         r[row] = rr;
@@ -364,7 +372,7 @@ int prfdd_csrm_cheby_residual(double *r, double *t, const prfdd_csr_matrix *A, c
 int prfdd_csrm_restrict_cheby_residual(double *f, double *r, double *t, const prfdd_csr_matrix *R, const double *v, const double *ds, double c_hi, prfdd_stream_t stream)
 {
     // f = R v fused with the zero-guess head of the coarse level's smoothing: r = ds f, t = ds (c_hi r)
-    return spmv(*R, v, 0, R->num_rows, S(stream), [=] __device__(int row, double ax) {
+    return spmv(*R, v, 0, R->num_rows, S(stream), 32.0, [=] __device__(int row, double ax) {
         const double d = ds[row];
         const double rr = d * ax;
         f[row] = ax;
@@ -378,16 +386,16 @@ int prfdd_csrm_cheby_step(double *u, double *t_out, const prfdd_csr_matrix *A, c
     if (last)
     {
         if (u_is_zero)
-            return spmv(*A, t_in, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) {
+            return spmv(*A, t_in, 0, A->num_rows, S(stream), 24.0, [=] __device__(int row, double ax) {
                 const double d = ds[row];
                 u[row] = d * (c * r[row] + d * ax);
             });
-        return spmv(*A, t_in, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) {
+        return spmv(*A, t_in, 0, A->num_rows, S(stream), 32.0, [=] __device__(int row, double ax) {
             const double d = ds[row];
             u[row] += d * (c * r[row] + d * ax);
         });
     }
-    return spmv(*A, t_in, 0, A->num_rows, S(stream), [=] __device__(int row, double ax) {
+    return spmv(*A, t_in, 0, A->num_rows, S(stream), 24.0, [=] __device__(int row, double ax) {
         const double d = ds[row];
         t_out[row] = d * (c * r[row] + d * ax);
     });
@@ -446,7 +454,7 @@ int prfdd_dense_solve(double *x, const double *Ainv, const double *b, int n, prf
 {
     if (n <= 0) return 0;
     k_dense_solve<<<(n + 7) / 8, 256, 0, S(stream)>>>(x, Ainv, b, n);
-    return launched();
+    return launched(8.0 * n * (double)n + 16.0 * n);
 }
 
 } // extern "C"

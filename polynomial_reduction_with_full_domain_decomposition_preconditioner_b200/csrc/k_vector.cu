@@ -10,6 +10,7 @@
 namespace prfdd
 {
 long long g_launch_count = 0;
+double g_algorithmic_bytes = 0.0;
 
 constexpr int kThreads = 256;
 constexpr int kRedThreads = 256;
@@ -26,12 +27,13 @@ __global__ void __launch_bounds__(kThreads) k_map(long long n, F f)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
 }
 
+// bpe: algorithmic bytes per element (every operand of the element-wise kernel once)
 template <class F>
-static int map(long long n, cudaStream_t st, F f)
+static int map(long long n, cudaStream_t st, double bpe, F f)
 {
     if (n <= 0) return 0;
     k_map<<<stream_grid(n, kThreads, 2, 8), kThreads, 0, st>>>(n, f);
-    return launched();
+    return launched(bpe * (double)n);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -111,14 +113,14 @@ __global__ void __launch_bounds__(kRedThreads) k_reduce(long long n, F f, double
 }
 
 template <int K, class F>
-static int reduce(prfdd_reduce_ws *ws, double *out, int out_stride, long long n, cudaStream_t st, F f)
+static int reduce(prfdd_reduce_ws *ws, double *out, int out_stride, long long n, cudaStream_t st, double bpe, F f)
 {
     static_assert(K <= kRedMaxK, "too many fused sums");
     if (ws == nullptr) return -2;
     int grid = stream_grid(n > 0 ? n : 1, kRedThreads, 4, 4);
     if (grid > kRedMaxBlocks) grid = kRedMaxBlocks;
     k_reduce<K><<<grid, kRedThreads, 0, st>>>(n, f, ws->partials, ws->counter, out, out_stride);
-    return launched();
+    return launched(bpe * (double)n);
 }
 } // namespace prfdd
 
@@ -147,6 +149,9 @@ int prfdd_reduce_ws_destroy(prfdd_reduce_ws *ws)
     return 0;
 }
 
+double prfdd_algorithmic_bytes(void) { return g_algorithmic_bytes; }
+void prfdd_algorithmic_bytes_reset(void) { g_algorithmic_bytes = 0.0; }
+void prfdd_algorithmic_bytes_add(double bytes) { g_algorithmic_bytes += bytes; }
 long long prfdd_launch_count(void) { return g_launch_count; }
 void prfdd_launch_count_reset(void) { g_launch_count = 0; }
 void prfdd_launch_count_add(long long n) { g_launch_count += n; }
@@ -154,32 +159,32 @@ void prfdd_launch_count_add(long long n) { g_launch_count += n; }
 // ------------------------------------------------------------------------------ math.okl
 int prfdd_set_to_value(double *u, double alpha, int n, int offset, prfdd_stream_t stream)
 {
-    return map(n, S(stream), [=] __device__(long long i) { u[i + offset] = alpha; });
+    return map(n, S(stream), 8.0, [=] __device__(long long i) { u[i + offset] = alpha; });
 }
 
 int prfdd_vector_set_to_value(double *data, double value, int size, prfdd_stream_t stream)
 {
-    return map(size, S(stream), [=] __device__(long long i) { data[i] = value; });
+    return map(size, S(stream), 8.0, [=] __device__(long long i) { data[i] = value; });
 }
 
 int prfdd_invert_vector_elements(double *u, int n, prfdd_stream_t stream)
 {
-    return map(n, S(stream), [=] __device__(long long i) { u[i] = 1.0 / u[i]; });
+    return map(n, S(stream), 16.0, [=] __device__(long long i) { u[i] = 1.0 / u[i]; });
 }
 
 int prfdd_vector_vector_addition(double *uv, double alpha, const double *u, double beta, const double *v, int n, prfdd_stream_t stream)
 {
-    return map(n, S(stream), [=] __device__(long long i) { uv[i] = alpha * u[i] + beta * v[i]; });
+    return map(n, S(stream), 24.0, [=] __device__(long long i) { uv[i] = alpha * u[i] + beta * v[i]; });
 }
 
 int prfdd_vector_scaling(double *au, double alpha, const double *u, int n, prfdd_stream_t stream)
 {
-    return map(n, S(stream), [=] __device__(long long i) { au[i] = alpha * u[i]; });
+    return map(n, S(stream), 16.0, [=] __device__(long long i) { au[i] = alpha * u[i]; });
 }
 
 int prfdd_vector_scaling_dev(double *au, const double *num, const double *den, const double *u, int n, prfdd_stream_t stream)
 {
-    return map(n, S(stream), [=] __device__(long long i) {
+    return map(n, S(stream), 16.0, [=] __device__(long long i) {
         double a = den ? (*num) / (*den) : (*num);
         au[i] = a * u[i];
     });
@@ -197,7 +202,7 @@ int prfdd_multi_axpy_dev(double *y, const double *const *X, const double *coef, 
     for (int i = 0; i < count; i++) pk.p[i] = X[i];
     // y = 1.0*y + (sign*c_i) X_i, i ascending: the same chain as the reference's sequence of
     // vector_vector_addition calls (domain.tpp:817-822, 902-907; subdomain.tpp:4396-4401, 4473-4478)
-    return map(n, S(stream), [=] __device__(long long i) {
+    return map(n, S(stream), 8.0 * (count + 2), [=] __device__(long long i) {
         double acc = y[i];
         for (int k = 0; k < count; k++)
         {
@@ -211,12 +216,12 @@ int prfdd_multi_axpy_dev(double *y, const double *const *X, const double *coef, 
 // ---------------------------------------------------------------- domain.okl element-wise
 int prfdd_initialize_arrays(double *u_k, double *r_k, const double *f, int n, prfdd_stream_t stream)
 {
-    return map(n, S(stream), [=] __device__(long long i) { u_k[i] = 0.0; r_k[i] = f[i]; });
+    return map(n, S(stream), 24.0, [=] __device__(long long i) { u_k[i] = 0.0; r_k[i] = f[i]; });
 }
 
 int prfdd_solution_and_residual_update(double *u_k, double *r_kp1, const double *r_k, const double *p_k, const double *q_k, double alpha_k, int n, prfdd_stream_t stream)
 {
-    return map(n, S(stream), [=] __device__(long long i) {
+    return map(n, S(stream), 48.0, [=] __device__(long long i) {
         u_k[i] += alpha_k * p_k[i];
         r_kp1[i] = r_k[i] - alpha_k * q_k[i];
     });
@@ -224,7 +229,7 @@ int prfdd_solution_and_residual_update(double *u_k, double *r_kp1, const double 
 
 int prfdd_solution_and_residual_update_dev(double *u_k, double *r_kp1, const double *r_k, const double *p_k, const double *q_k, const double *num, const double *den, int n, prfdd_stream_t stream)
 {
-    return map(n, S(stream), [=] __device__(long long i) {
+    return map(n, S(stream), 48.0, [=] __device__(long long i) {
         double alpha_k = (*num) / (*den);
         u_k[i] += alpha_k * p_k[i];
         r_kp1[i] = r_k[i] - alpha_k * q_k[i];
@@ -233,7 +238,7 @@ int prfdd_solution_and_residual_update_dev(double *u_k, double *r_kp1, const dou
 
 int prfdd_residual_and_search_update(double *p_k, double *r_k, const double *z_k, const double *r_kp1, double beta_k, int n, prfdd_stream_t stream)
 {
-    return map(n, S(stream), [=] __device__(long long i) {
+    return map(n, S(stream), 40.0, [=] __device__(long long i) {
         p_k[i] = z_k[i] + beta_k * p_k[i];
         r_k[i] = r_kp1[i];
     });
@@ -241,7 +246,7 @@ int prfdd_residual_and_search_update(double *p_k, double *r_k, const double *z_k
 
 int prfdd_residual_and_search_update_dev(double *p_k, double *r_k, const double *z_k, const double *r_kp1, const double *num, const double *den, int n, prfdd_stream_t stream)
 {
-    return map(n, S(stream), [=] __device__(long long i) {
+    return map(n, S(stream), 40.0, [=] __device__(long long i) {
         double beta_k = (*num) / (*den);
         p_k[i] = z_k[i] + beta_k * p_k[i];
         r_k[i] = r_kp1[i];
@@ -250,18 +255,18 @@ int prfdd_residual_and_search_update_dev(double *p_k, double *r_k, const double 
 
 int prfdd_copy_from_domain_data(double *u, const double *v, int num_points, prfdd_stream_t stream)
 {
-    return map(num_points, S(stream), [=] __device__(long long i) { u[i] = v[i]; });
+    return map(num_points, S(stream), 16.0, [=] __device__(long long i) { u[i] = v[i]; });
 }
 
 int prfdd_copy_to_domain_data(double *u, const double *v, int num_points, prfdd_stream_t stream)
 {
-    return map(num_points, S(stream), [=] __device__(long long i) { u[i] = v[i]; });
+    return map(num_points, S(stream), 16.0, [=] __device__(long long i) { u[i] = v[i]; });
 }
 
 // ---------------------------------------------------------------- AMG/kernels.cu
 int prfdd_main_scaled_residual(double *Sr, double *w, const double *f_m_Au, const double *Sv, double alpha, int size, prfdd_stream_t stream)
 {
-    return map(size, S(stream), [=] __device__(long long i) {
+    return map(size, S(stream), 32.0, [=] __device__(long long i) {
         double s = Sv[i] * f_m_Au[i];
         Sr[i] = s;
         w[i] = alpha * s;
@@ -270,7 +275,7 @@ int prfdd_main_scaled_residual(double *Sr, double *w, const double *f_m_Au, cons
 
 int prfdd_main_polynomial_evaluation(double *w, double *v, const double *r, const double *D_val, double alpha, int size, prfdd_stream_t stream)
 {
-    return map(size, S(stream), [=] __device__(long long i) {
+    return map(size, S(stream), 40.0, [=] __device__(long long i) {
         double t = v[i] * D_val[i];
         v[i] = t;
         w[i] = alpha * r[i] + t;
@@ -279,17 +284,17 @@ int prfdd_main_polynomial_evaluation(double *w, double *v, const double *r, cons
 
 int prfdd_main_update_field(double *u, const double *w, const double *D_val, int size, prfdd_stream_t stream)
 {
-    return map(size, S(stream), [=] __device__(long long i) { u[i] += D_val[i] * w[i]; });
+    return map(size, S(stream), 32.0, [=] __device__(long long i) { u[i] += D_val[i] * w[i]; });
 }
 
 int prfdd_vector_multiplication(double *uv, const double *u, const double *v, int size, prfdd_stream_t stream)
 {
-    return map(size, S(stream), [=] __device__(long long i) { uv[i] = u[i] * v[i]; });
+    return map(size, S(stream), 24.0, [=] __device__(long long i) { uv[i] = u[i] * v[i]; });
 }
 
 int prfdd_cheby_order1(double *u, const double *r, const double *ds, double c, int u_is_zero, int size, prfdd_stream_t stream)
 {
-    return map(size, S(stream), [=] __device__(long long i) {
+    return map(size, S(stream), (u_is_zero ? 24.0 : 32.0), [=] __device__(long long i) {
         double w = ds[i] * (c * r[i]);
         u[i] = u_is_zero ? w : u[i] + w;
     });
@@ -298,12 +303,12 @@ int prfdd_cheby_order1(double *u, const double *r, const double *ds, double c, i
 // ---------------------------------------------------------------- reductions
 int prfdd_residual_norm(prfdd_reduce_ws *ws, double *out, const double *r_k, const double *QQt_r_k, const double *mask, int n, prfdd_stream_t stream)
 {
-    return reduce<1>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) { a[0] += r_k[i] * QQt_r_k[i] * mask[i]; });
+    return reduce<1>(ws, out, 1, n, S(stream), 24.0, [=] __device__(long long i, double(&a)[1]) { a[0] += r_k[i] * QQt_r_k[i] * mask[i]; });
 }
 
 int prfdd_projection_inner_products(prfdd_reduce_ws *ws, double *out, const double *z_k, const double *r_k, const double *p_k, const double *q_k, int n, prfdd_stream_t stream)
 {
-    return reduce<2>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[2]) {
+    return reduce<2>(ws, out, 1, n, S(stream), 32.0, [=] __device__(long long i, double(&a)[2]) {
         a[0] += z_k[i] * r_k[i];
         a[1] += p_k[i] * q_k[i];
     });
@@ -311,19 +316,19 @@ int prfdd_projection_inner_products(prfdd_reduce_ws *ws, double *out, const doub
 
 int prfdd_inner_product_flexible(prfdd_reduce_ws *ws, double *out, const double *r_k, const double *r_kp1, const double *z_k, int n, prfdd_stream_t stream)
 {
-    return reduce<1>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) { a[0] += (r_kp1[i] - r_k[i]) * z_k[i]; });
+    return reduce<1>(ws, out, 1, n, S(stream), 24.0, [=] __device__(long long i, double(&a)[1]) { a[0] += (r_kp1[i] - r_k[i]) * z_k[i]; });
 }
 
 int prfdd_inner_product(prfdd_reduce_ws *ws, double *out, const double *u_k, const double *v_k, const double *mask, int n, prfdd_stream_t stream)
 {
-    return reduce<1>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) { a[0] += u_k[i] * v_k[i] * mask[i]; });
+    return reduce<1>(ws, out, 1, n, S(stream), 24.0, [=] __device__(long long i, double(&a)[1]) { a[0] += u_k[i] * v_k[i] * mask[i]; });
 }
 
 int prfdd_weighted_inner_product(prfdd_reduce_ws *ws, double *out, const double *u, const double *v, const double *w, int n, prfdd_stream_t stream)
 {
     if (w)
-        return reduce<1>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) { a[0] += u[i] * v[i] * w[i]; });
-    return reduce<1>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) { a[0] += u[i] * v[i]; });
+        return reduce<1>(ws, out, 1, n, S(stream), (8.0 * ((u == v ? 1 : 2) + (w ? 1 : 0))), [=] __device__(long long i, double(&a)[1]) { a[0] += u[i] * v[i] * w[i]; });
+    return reduce<1>(ws, out, 1, n, S(stream), (8.0 * ((u == v ? 1 : 2) + (w ? 1 : 0))), [=] __device__(long long i, double(&a)[1]) { a[0] += u[i] * v[i]; });
 }
 
 int prfdd_multi_inner_product(prfdd_reduce_ws *ws, double *out, const double *u, const double *const *V, const double *w, int count, int n, prfdd_stream_t stream)
@@ -336,22 +341,22 @@ int prfdd_multi_inner_product(prfdd_reduce_ws *ws, double *out, const double *u,
         const double *v0 = V[base], *v1 = c > 1 ? V[base + 1] : V[base], *v2 = c > 2 ? V[base + 2] : V[base], *v3 = c > 3 ? V[base + 3] : V[base];
         double *o = out + base;
         if (c == 1)
-            rc = reduce<1>(ws, o, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) { a[0] += u[i] * v0[i] * (w ? w[i] : 1.0); });
+            rc = reduce<1>(ws, o, 1, n, S(stream), (8.0 * (c + 1 + (w ? 1 : 0))), [=] __device__(long long i, double(&a)[1]) { a[0] += u[i] * v0[i] * (w ? w[i] : 1.0); });
         else if (c == 2)
-            rc = reduce<2>(ws, o, 1, n, S(stream), [=] __device__(long long i, double(&a)[2]) {
+            rc = reduce<2>(ws, o, 1, n, S(stream), (8.0 * (c + 1 + (w ? 1 : 0))), [=] __device__(long long i, double(&a)[2]) {
                 double uw = u[i] * (w ? w[i] : 1.0);
                 a[0] += uw * v0[i];
                 a[1] += uw * v1[i];
             });
         else if (c == 3)
-            rc = reduce<3>(ws, o, 1, n, S(stream), [=] __device__(long long i, double(&a)[3]) {
+            rc = reduce<3>(ws, o, 1, n, S(stream), (8.0 * (c + 1 + (w ? 1 : 0))), [=] __device__(long long i, double(&a)[3]) {
                 double uw = u[i] * (w ? w[i] : 1.0);
                 a[0] += uw * v0[i];
                 a[1] += uw * v1[i];
                 a[2] += uw * v2[i];
             });
         else
-            rc = reduce<4>(ws, o, 1, n, S(stream), [=] __device__(long long i, double(&a)[4]) {
+            rc = reduce<4>(ws, o, 1, n, S(stream), (8.0 * (c + 1 + (w ? 1 : 0))), [=] __device__(long long i, double(&a)[4]) {
                 double uw = u[i] * (w ? w[i] : 1.0);
                 a[0] += uw * v0[i];
                 a[1] += uw * v1[i];
@@ -370,7 +375,7 @@ int prfdd_orthogonalize_norm(prfdd_reduce_ws *ws, double *out, double *aq, const
     if (count > 32) return -3;
     PtrPack pk;
     for (int i = 0; i < count; i++) pk.p[i] = aV[i];
-    return reduce<1>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) {
+    return reduce<1>(ws, out, 1, n, S(stream), 8.0 * (count + 3), [=] __device__(long long i, double(&a)[1]) {
         double acc = aq[i];
         for (int k = 0; k < count; k++)
         {
@@ -391,7 +396,7 @@ int prfdd_arnoldi_next(double *V_next, const double *q, const double *const *V, 
     if (count > 32) return -3;
     PtrPack pk;
     for (int i = 0; i < count; i++) pk.p[i] = V[i];
-    return map((long long)n + n_assembled, S(stream), [=] __device__(long long i) {
+    return map((long long)n + n_assembled, S(stream), (8.0 * (count + 2) * n + 16.0 * n_assembled) / (double)((long long)n + n_assembled > 0 ? (long long)n + n_assembled : 1), [=] __device__(long long i) {
         const double a = *scale;
         if (i < n)
         {
@@ -410,7 +415,7 @@ int prfdd_arnoldi_next(double *V_next, const double *q, const double *const *V, 
 
 int prfdd_weighted_projection_inner_products(prfdd_reduce_ws *ws, double *out, const double *z_k, const double *r_k, const double *p_k, const double *q_k, const double *weight, int n, prfdd_stream_t stream)
 {
-    return reduce<2>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[2]) {
+    return reduce<2>(ws, out, 1, n, S(stream), 40.0, [=] __device__(long long i, double(&a)[2]) {
         a[0] += z_k[i] * r_k[i] * weight[i];
         a[1] += p_k[i] * q_k[i] * weight[i];
     });
@@ -418,7 +423,7 @@ int prfdd_weighted_projection_inner_products(prfdd_reduce_ws *ws, double *out, c
 
 int prfdd_search_update_inner_product(prfdd_reduce_ws *ws, double *out, const double *r_k, const double *r_kp1, const double *z_k, const double *weight, int n, prfdd_stream_t stream)
 {
-    return reduce<1>(ws, out, 1, n, S(stream), [=] __device__(long long i, double(&a)[1]) { a[0] += (r_kp1[i] - r_k[i]) * z_k[i] * weight[i]; });
+    return reduce<1>(ws, out, 1, n, S(stream), 32.0, [=] __device__(long long i, double(&a)[1]) { a[0] += (r_kp1[i] - r_k[i]) * z_k[i] * weight[i]; });
 }
 
 } // extern "C"

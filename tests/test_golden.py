@@ -134,10 +134,12 @@ def test_cuda_operator_matches_reference_vectors(G, dim, N):
     n = N + 1
     E = u.size // n ** dim
     du, dD, dG, dAu = G.dev(u), G.dev(D), [G.dev(np.ascontiguousarray(g)) for g in Gs], G.dev(np.full(u.size, np.nan))
-    assert G.lib.prfdd_stiffness_matrix(G.p(dAu), G.p(du), G.p(dD), G.ptr_array(dG), C.c_int(E), C.c_int(n), C.c_int(dim), G.stream()) == 0
-    G.sync()
     scale = (np.abs(np.stack(Gs)).max() * np.abs(u).max() * np.abs(D).max() ** 2) * n * n
-    assert np.abs(G.host(dAu) - Au).max() <= 50 * TOL * scale
+    Dh = np.ascontiguousarray(D, dtype=np.float64)
+    for host_d in (None, Dh.ctypes.data_as(C.c_void_p)):      # generic kernel, then the constant-bank / bulk-async kernels
+        assert G.lib.prfdd_stiffness_matrix_hd(G.p(dAu), G.p(du), G.p(dD), host_d, G.ptr_array(dG), C.c_int(E), C.c_int(n), C.c_int(dim), G.stream()) == 0
+        G.sync()
+        assert np.abs(G.host(dAu) - Au).max() <= 50 * TOL * scale
 
 
 @pytest.mark.gpu

@@ -52,12 +52,28 @@ def test_stiffness_matrix(G, dim, N):
     D = _D(n)
     ref = _oracle_ax(u, Gs, D, E, N, dim)
     du, dD, dG, dAu = G.dev(u), G.dev(D), [G.dev(g) for g in Gs], G.dev(np.full(npts, np.nan))
+    scale = np.abs(ref).max()
+    # device D only (generic kernel, D read from device memory), then with the host copy of D (constant-bank kernels, bulk-async for n = 6, 8)
     rc = G.lib.prfdd_stiffness_matrix(G.p(dAu), G.p(du), G.p(dD), G.ptr_array(dG), C.c_int(E), C.c_int(n), C.c_int(dim), G.stream())
     assert rc == 0
     G.sync()
-    out = G.host(dAu)
-    scale = np.abs(ref).max()
-    assert np.abs(out - ref).max() <= 50 * TOL * scale
+    assert np.abs(G.host(dAu) - ref).max() <= 50 * TOL * scale
+    dAu2 = G.dev(np.full(npts, np.nan))
+    rc = G.lib.prfdd_stiffness_matrix_hd(G.p(dAu2), G.p(du), G.p(dD), D.ctypes.data_as(C.c_void_p), G.ptr_array(dG), C.c_int(E), C.c_int(n), C.c_int(dim), G.stream())
+    assert rc == 0
+    G.sync()
+    assert np.abs(G.host(dAu2) - ref).max() <= 50 * TOL * scale
+    if dim == 3 and n in (6, 8):
+        # operands at an odd double offset: the bulk-async kernel must not be chosen (16-byte alignment), the result must not change
+        pad = lambda a: G.dev(np.concatenate([[0.0], a]))
+        du_o, dG_o = pad(u), [pad(g) for g in Gs]
+        off = lambda t: C.c_void_p(t.data_ptr() + 8)
+        gp = (C.c_void_p * 6)(*[t.data_ptr() + 8 for t in dG_o])
+        dAu3 = G.dev(np.full(npts, np.nan))
+        rc = G.lib.prfdd_stiffness_matrix_hd(G.p(dAu3), off(du_o), G.p(dD), D.ctypes.data_as(C.c_void_p), gp, C.c_int(E), C.c_int(n), C.c_int(dim), G.stream())
+        assert rc == 0
+        G.sync()
+        assert np.abs(G.host(dAu3) - ref).max() <= 50 * TOL * scale
 
 
 def test_stiffness_matrix_region_mixed_degrees(G):
@@ -91,6 +107,12 @@ def test_stiffness_matrix_region_mixed_degrees(G):
     assert rc == 0
     G.sync()
     assert np.abs(G.host(dAu) - ref).max() <= 50 * TOL * np.abs(ref).max()
+    hD = (C.c_void_p * 3)(*[d.ctypes.data for d in Ds])
+    dAu2 = G.dev(np.zeros(npts))
+    rc = G.lib.prfdd_stiffness_matrix_region_hd(G.p(dAu2), G.p(du), G.ptr_array(dG), C.c_int(3), fp, ne, nn, G.ptr_array(dDs), hD, C.c_int(dim), G.stream())
+    assert rc == 0
+    G.sync()
+    assert np.abs(G.host(dAu2) - ref).max() <= 50 * TOL * np.abs(ref).max()
 
 
 @pytest.mark.parametrize("dim,nf,nc", [(2, 8, 5), (2, 5, 2), (3, 8, 5), (3, 5, 2), (3, 8, 2), (3, 10, 7), (3, 16, 9)])
