@@ -14,6 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libprfdd_b200.so")
 EXE = os.path.join(HERE, "poisson")
+COMPAT = os.path.join(HERE, "libprfdd_compat.so")   # the reference's own five extern "C" names (include/prfdd_compat.h)
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -66,6 +67,13 @@ def build(verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("poisson link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    csrc = os.path.join(CSRC, "compat.cpp")
+    if (not os.path.exists(COMPAT)) or os.path.getmtime(csrc) > os.path.getmtime(COMPAT) or os.path.getmtime(LIB) > os.path.getmtime(COMPAT):
+        cmd = ["nvcc"] + ARCH + ["-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared", "-x", "cu", csrc, "-o", COMPAT,
+               "-L" + HERE, "-lprfdd_b200", "-Xlinker", "-rpath=$ORIGIN", "-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("compat link failed:\n%s\n%s" % (r.stdout, r.stderr))
     if verbose:
         print("built", LIB)
     return LIB

@@ -20,11 +20,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pc", type=int, default=0)
     ap.add_argument("--dim", type=int, default=3)
-    ap.add_argument("--nel", type=int, default=4)
+    ap.add_argument("--nel", default="4", help="elements per side, or nx,ny[,nz]")
     ap.add_argument("--degree", dest="N", type=int, default=5)
     ap.add_argument("--reduction", dest="r", type=int, default=2)
     ap.add_argument("--eps", type=float, default=0.04)
     a = ap.parse_args()
+    a.nel = tuple(int(x) for x in a.nel.split(",")) if "," in a.nel else int(a.nel)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -101,7 +102,7 @@ def main():
                 # the same numbers computed by the oracle in the build container (tests/golden/solve_histories.json), if this case is there
                 import json
                 gold = [c for c in json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solve_histories.json")))
-                        if (c["dim"], c["nel"], c["N"], c["r"], c["eps"], c["ranks"], c["solver"]) == (a.dim, a.nel, a.N, a.r, a.eps, world, solver_id)]
+                        if (c["dim"], c["nel"], c["N"], c["r"], c["eps"], c["ranks"], c["solver"]) == (a.dim, list(a.nel) if isinstance(a.nel, tuple) else a.nel, a.N, a.r, a.eps, world, solver_id)]
                 for c in gold:
                     ref = np.array(c["history"])
                     assert gathered[0]["nit"] == c["iterations"] and np.abs(gathered[0]["hist"] - ref).max() <= 1e-9 * ref[0]

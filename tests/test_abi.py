@@ -65,3 +65,46 @@ def test_no_oracle_in_product():
     lib = os.path.join(pkg, "libprfdd_b200.so")
     deps = subprocess.run(["ldd", lib], capture_output=True, text=True).stdout
     assert "oracle" not in deps and "libref_okl" not in deps, deps
+
+
+def test_reference_host_code_links_against_the_compat_library(tmp_path):
+    """include/prfdd_compat.h: a stub that declares the five launchers exactly as the reference's host code does (subdomain.tpp:17,
+    42-43, 70; AMG/vector.cpp:71) and calls the OKL-named wrappers compiles and LINKS against libprfdd_compat.so + libprfdd_b200.so
+    (no GPU needed: nothing is executed)"""
+    import shutil
+    import subprocess
+    pkg = os.path.join(ROOT, "polynomial_reduction_with_full_domain_decomposition_preconditioner_b200")
+    if not os.path.exists(os.path.join(pkg, "libprfdd_compat.so")) or shutil.which("nvcc") is None:
+        pytest.skip("compat library not built")
+    src = tmp_path / "stub.cpp"
+    src.write_text(r"""
+#include <cuda_runtime.h>
+typedef double Float;
+// the reference's own declarations, verbatim in form (extern "C", void, trailing cudaStream_t)
+extern "C" void vector_set_to_value(Float *data, const Float value, const int size, cudaStream_t stream);
+extern "C" void main_scaled_residual(Float *Sr, Float *w, const Float *f_m_Au, const Float *S, const Float alpha, const int size, cudaStream_t stream);
+extern "C" void main_polynomial_evaluation(Float *w, Float *v, const Float *r, const Float *D_val, const Float alpha, const int size, cudaStream_t stream);
+extern "C" void main_update_field(Float *u, const Float *w, const Float *D_val, const int size, cudaStream_t stream);
+extern "C" void vector_multiplication(Float *uv, const Float *u, const Float *v, const int size, cudaStream_t stream);
+#include "prfdd_compat.h"
+int main(int argc, char **)
+{
+    if (argc > 100)  // never true: the calls only have to link
+    {
+        double *p = nullptr; const int *ip = nullptr; cudaStream_t s = nullptr;
+        vector_set_to_value(p, 0.0, 0, s); main_scaled_residual(p, p, p, p, 1.0, 0, s); main_polynomial_evaluation(p, p, p, p, 1.0, 0, s);
+        main_update_field(p, p, p, 0, s); vector_multiplication(p, p, p, 0, s);
+        prfdd_okl::vector_vector_addition(p, 1.0, p, 1.0, p, 0, s); prfdd_okl::multiply(p, ip, ip, p, p, 0, s);
+        prfdd_okl::multiply_range(p, ip, ip, p, p, 0, 0, s); prfdd_okl::initialize_arrays(p, p, p, 0, s);
+        prfdd_okl::solution_and_residual_update(p, p, p, p, p, 1.0, 0, s); prfdd_okl::copy_to_domain_data(p, p, 0, s);
+    }
+    return 0;
+}
+""")
+    exe = tmp_path / "stub"
+    cmd = ["nvcc", "-std=c++17", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L" + pkg, "-lprfdd_compat", "-lprfdd_b200", "-Xlinker", "-rpath=" + pkg, "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    nm = subprocess.run(["nm", "-D", "--defined-only", os.path.join(pkg, "libprfdd_compat.so")], capture_output=True, text=True).stdout
+    for name in ("vector_set_to_value", "main_scaled_residual", "main_polynomial_evaluation", "main_update_field", "vector_multiplication"):
+        assert (" T " + name) in nm, name
