@@ -476,6 +476,15 @@ def main():
         phases = {k: round(1e3 * float(v), 3) for k, v in zip(PHASE_KEYS, t.tolist()) if v > 0}
         phases["_note"] = "ms of one fenced solve, max over ranks (fencing and the absence of graph replay inflate small phases)"
 
+    vprof = None
+    if args.phases and use_pc:
+        mine = S.profile_vcycle(5)
+        if world > 1:
+            allp = [None] * world
+            dist.all_gather_object(allp, mine)
+            vprof = {"rank0": allp[0].splitlines(), "rank%d" % (world - 1): allp[-1].splitlines()}
+        else:
+            vprof = {"rank0": mine.splitlines()}
     amg_rows = [int(x) for x in S.get_array("AMG_LEVEL_ROWS")] if use_pc else []
     amg_nnz = [int(x) for x in S.get_array("AMG_LEVEL_NNZ")] if use_pc else []
     sizes = None
@@ -526,6 +535,8 @@ def main():
             line["sizes"] = sizes
         if phases:
             line["phases"] = phases
+        if vprof:
+            line["vcycle_profile"] = {"columns": "level what rows nnz us algorithmic_MB GB/s (every launch of one V-cycle between CUDA events, average of 5 cycles)", **vprof}
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

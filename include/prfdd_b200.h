@@ -455,6 +455,10 @@ int prfdd_solver_apply(prfdd_solver *s, int what, const double *in_host, double 
  * events on the solver's stream.  out[0] = average ms per launch, out[1] = average algorithmic bytes per launch
  * (12*nnz + 4*(rows+1) + 5*8*rows), out[2] = rows of level 0, out[3] = nnz of level 0, out[4] = rows of level 1, out[5] = nnz of level 1 */
 int prfdd_solver_time_spmv(prfdd_solver *s, int reps, double out[6]);
+/* per-launch profile of the AMG V-cycle of this rank (average of `reps` cycles, every launch bracketed by CUDA events on the solver's
+ * stream): a text table, one line per launch -- "level what rows nnz microseconds algorithmic_MB GB/s" -- and a total line.
+ * Returns 0, or -(needed capacity). */
+int prfdd_solver_profile_vcycle(prfdd_solver *s, int reps, char *text, int capacity);
 /* field output (Domain::output, domain.tpp:373-524; the reference writes Silo, compiled out by VISUALIZATION 0): the low-order
  * cell mesh (every GLL cell a quad / hexahedron) with node-centred fields as a legacy-VTK unstructured grid.  Host arrays,
  * element-major points, n = points per direction. */

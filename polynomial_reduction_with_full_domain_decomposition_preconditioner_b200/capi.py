@@ -151,5 +151,11 @@ class Solver:
         """u_star, f, u of this rank's elements -> <name>_<rank>.vtk (poisson.cpp:233-235)"""
         check(lib().prfdd_solver_output(self.h, name.encode()), "output")
 
+    def profile_vcycle(self, reps=5):
+        """per-launch table of this rank's AMG V-cycle (prfdd_solver_profile_vcycle)"""
+        buf = C.create_string_buffer(1 << 16)
+        check(lib().prfdd_solver_profile_vcycle(self.h, C.c_int(reps), buf, C.c_int(len(buf))), "profile_vcycle")
+        return buf.value.decode()
+
     def timer(self, key):
         return float(lib().prfdd_solver_timer_total(self.h, key.encode()))

@@ -712,6 +712,32 @@ class Hierarchy
 
     int num_levels() const { return (int)levels.size(); }
 
+    // Per-launch profile of one cycle (prfdd_solver_profile_vcycle): when `prof` is set every launch of the cycle is bracketed by
+    // CUDA events on the stream; read back after the cycle.  Off (nullptr) in normal operation and under graph capture.
+    struct ProfileRec
+    {
+        int level;
+        const char *what;
+        cudaEvent_t e0, e1;
+        double bytes;
+        int rows, nnz;
+    };
+    std::vector<ProfileRec> *prof = nullptr;
+    template <class F>
+    void timed(int level, const char *what, int rows, int nnz, F launch)
+    {
+        if (!prof) { dev::check_rc(launch(), what); return; }
+        ProfileRec r{level, what, nullptr, nullptr, 0.0, rows, nnz};
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        const double b0 = prfdd_algorithmic_bytes();
+        cudaEventRecord(r.e0, prfdd_host::device.stream);
+        dev::check_rc(launch(), what);
+        cudaEventRecord(r.e1, prfdd_host::device.stream);
+        r.bytes = prfdd_algorithmic_bytes() - b0;
+        prof->push_back(r);
+    }
+
     void setup(HostCSR A0, int cheby_order_, int max_coarse = 9, double theta = 0.25, int pmax = 4, int max_levels = 25, bool on_device = true)
     {
         cheby_order = std::max(1, std::min(4, cheby_order_)); // subdomain.tpp:3477-3478
@@ -806,27 +832,30 @@ class Hierarchy
     // hypre-style Chebyshev smoothing: r = ds(f - A u); w = c[k-1] r; for p = k-2..0: w = c[p] r + ds A ds w; u += ds w
     void smooth(Level &L, bool u_is_zero, bool residual_done = false)
     {
+        const int lv = (int)(&L - levels.data());
         cudaStream_t st = prfdd_host::device.stream;
         const int k = cheby_order;
         double *u = L.u.as<double>(), *r = L.r.as<double>(), *t0 = L.t0.as<double>(), *t1 = L.t1.as<double>();
         const double *ds = L.ds.as<double>(), *f = L.f.as<double>();
         // residual_done: the restriction that produced f already wrote r and t0 (prfdd_restrict_cheby_residual)
-        if (!residual_done) dev::check_rc(prfdd_csrm_cheby_residual(r, t0, &L.dA.desc, u_is_zero ? nullptr : u, f, ds, L.coefs[k - 1], st), "cheby_residual");
+        if (!residual_done) timed(lv, u_is_zero ? "cheby_residual(u=0)" : "cheby_residual", L.n, L.dA.nnz, [&] { return prfdd_csrm_cheby_residual(r, t0, &L.dA.desc, u_is_zero ? nullptr : u, f, ds, L.coefs[k - 1], st); });
         if (k == 1)
         {
-            dev::check_rc(prfdd_cheby_order1(u, r, ds, L.coefs[0], u_is_zero ? 1 : 0, L.n, st), "cheby_order1");
+            timed(lv, "cheby_order1", L.n, 0, [&] { return prfdd_cheby_order1(u, r, ds, L.coefs[0], u_is_zero ? 1 : 0, L.n, st); });
             return;
         }
         double *tin = t0, *tout = t1;
         for (int p = k - 2; p >= 0; p--)
         {
-            dev::check_rc(prfdd_csrm_cheby_step(u, tout, &L.dA.desc, tin, r, ds, L.coefs[p], p == 0 ? 1 : 0, u_is_zero ? 1 : 0, st), "cheby_step");
+            timed(lv, "cheby_step", L.n, L.dA.nnz, [&] { return prfdd_csrm_cheby_step(u, tout, &L.dA.desc, tin, r, ds, L.coefs[p], p == 0 ? 1 : 0, u_is_zero ? 1 : 0, st); });
             std::swap(tin, tout);
         }
     }
 
     // zero-guess cycle over the levels l0 .. coarsest: levels[l0].f -> levels[l0].u   (subdomain.tpp:4012-4139)
-    void cycle_from(int l0, bool first_guess_is_zero = true)
+    // head_done: the caller produced levels[l0].f with a product that also wrote the zero-guess head r = ds f, t0 = ds (c r)
+    // (prfdd_csrm_restrict_cheby_residual), so the first smoothing skips it
+    void cycle_from(int l0, bool first_guess_is_zero = true, bool head_done = false)
     {
         cudaStream_t st = prfdd_host::device.stream;
         const int nl = num_levels();
@@ -834,31 +863,31 @@ class Hierarchy
         for (int l = l0; l < bottom; l++)
         {
             Level &L = levels[l];
-            smooth(L, l > l0 || first_guess_is_zero, l > l0);
-            dev::check_rc(prfdd_csrm_residual(L.v.as<double>(), &L.dA.desc, L.u.as<double>(), L.f.as<double>(), st), "csr_residual");
+            smooth(L, l > l0 || first_guess_is_zero, l > l0 || (head_done && first_guess_is_zero));
+            timed(l, "csr_residual", L.n, L.dA.nnz, [&] { return prfdd_csrm_residual(L.v.as<double>(), &L.dA.desc, L.u.as<double>(), L.f.as<double>(), st); });
             Level &Lc = levels[l + 1];
             if (l + 1 < bottom) // the coarse level is smoothed next: fuse the head of that smoothing into the restriction
-                dev::check_rc(prfdd_csrm_restrict_cheby_residual(Lc.f.as<double>(), Lc.r.as<double>(), Lc.t0.as<double>(), &L.dR.desc, L.v.as<double>(),
-                                                                 Lc.ds.as<double>(), Lc.coefs[cheby_order - 1], st), "restrict + residual");
+                timed(l, "restrict+cheby_residual", Lc.n, L.dR.nnz, [&] { return prfdd_csrm_restrict_cheby_residual(Lc.f.as<double>(), Lc.r.as<double>(), Lc.t0.as<double>(), &L.dR.desc, L.v.as<double>(),
+                                                                 Lc.ds.as<double>(), Lc.coefs[cheby_order - 1], st); });
             else
-                dev::check_rc(prfdd_csrm_multiply(Lc.f.as<double>(), &L.dR.desc, L.v.as<double>(), st), "restrict");
+                timed(l, "restrict", Lc.n, L.dR.nnz, [&] { return prfdd_csrm_multiply(Lc.f.as<double>(), &L.dR.desc, L.v.as<double>(), st); });
         }
         Level &last = levels[bottom];
-        if (bottom == nl - 1) dev::check_rc(prfdd_dense_solve(last.u.as<double>(), Ainv.as<double>(), last.f.as<double>(), last.n, st), "dense_solve");
-        else dev::check_rc(prfdd_dense_solve(last.u.as<double>(), Bdense.as<double>(), last.f.as<double>(), last.n, st), "collapsed coarse levels");
+        if (bottom == nl - 1) timed(bottom, "dense_solve", last.n, 0, [&] { return prfdd_dense_solve(last.u.as<double>(), Ainv.as<double>(), last.f.as<double>(), last.n, st); });
+        else timed(bottom, "collapsed coarse levels (dense)", last.n, 0, [&] { return prfdd_dense_solve(last.u.as<double>(), Bdense.as<double>(), last.f.as<double>(), last.n, st); });
         for (int l = bottom; l > l0; l--)
         {
             Level &L = levels[l - 1];
             Level &Lc = levels[l];
-            dev::check_rc(prfdd_csrm_matvec(L.u.as<double>(), &L.dP.desc, Lc.u.as<double>(), 1.0, 1.0, st), "prolong");
+            timed(l - 1, "prolong", L.n, L.dP.nnz, [&] { return prfdd_csrm_matvec(L.u.as<double>(), &L.dP.desc, Lc.u.as<double>(), 1.0, 1.0, st); });
             smooth(L, false);
         }
     }
 
     // levels[0].f holds the right-hand side; result in levels[0].u
-    void vcycle(int num_vcycles)
+    void vcycle(int num_vcycles, bool head_done = false)
     {
-        for (int iter = 0; iter < num_vcycles; iter++) cycle_from(0, iter == 0);
+        for (int iter = 0; iter < num_vcycles; iter++) cycle_from(0, iter == 0, head_done && iter == 0);
     }
 };
 } // namespace amg

@@ -327,6 +327,11 @@ int prfdd_solver_apply(prfdd_solver *s, int what, const double *in_host, double 
     });
 }
 
+int prfdd_solver_profile_vcycle(prfdd_solver *s, int reps, char *text, int capacity)
+{
+    return guarded(s, [&]() { return s->subdomain ? s->subdomain->profile_vcycle(reps, text, capacity) : -1; });
+}
+
 int prfdd_solver_time_spmv(prfdd_solver *s, int reps, double out[6])
 {
     return guarded(s, [&]() { return s->subdomain ? s->subdomain->time_spmv(reps, out) : -1; });

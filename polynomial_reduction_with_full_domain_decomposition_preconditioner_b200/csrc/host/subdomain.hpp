@@ -233,6 +233,7 @@ class Subdomain
     long long get_array(int what, void *dst, long long cap);
     int apply(int what, const double *in_host, double *out_host);
     int time_spmv(int reps, double out[6]);
+    int profile_vcycle(int reps, char *text, int cap);
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -950,11 +951,17 @@ void Subdomain<DType>::low_order_preconditioner(const memory &z, const memory &r
         timer.stop("subdomain.preconditioner.assemble_subdomain");
         if (ns > 0) work_dev[0].slice(ne, ns).copyFrom(r.slice(npt, ns), ns * sizeof(DType));
     }
+    // interface assembly fused with the head of level 0's zero-guess smoothing: f = Qt_int a, r = ds f, t0 = ds (c r) in one pass
     timer.start("subdomain.preconditioner.assemble_composite");
-    Qt_int.multiply(L0.f, r_assembled ? *r_assembled : work_dev[0]);
+    const bool head = amg_fem.num_levels() > 1 && Qt_int.num_rows == L0.n && Qt_int.num_nnz > 0 && !Qt_int.unit_values;
+    if (head)
+        dev::check_rc(prfdd_csrm_restrict_cheby_residual(dp(L0.f), dp(L0.r), dp(L0.t0), &Qt_int.desc, dp(r_assembled ? *r_assembled : work_dev[0]), dp(L0.ds),
+                                                         L0.coefs[amg_fem.cheby_order - 1], st()), "Qt_int + smoothing head");
+    else
+        Qt_int.multiply(L0.f, r_assembled ? *r_assembled : work_dev[0]);
     timer.stop("subdomain.preconditioner.assemble_composite");
     timer.start("subdomain.preconditioner.down_leg_gpu");
-    amg_fem.vcycle(num_vcycles);
+    amg_fem.vcycle(num_vcycles, head);
     timer.stop("subdomain.preconditioner.down_leg_gpu");
     timer.start("subdomain.preconditioner.unassemble_composite");
     Q_int.multiply(work_dev[0], L0.u);
@@ -1366,6 +1373,48 @@ int Subdomain<DType>::time_spmv(int reps, double out[6])
     }
     out[0] = ms / reps;
     out[1] = bytes;
+    return 0;
+}
+
+// one V-cycle with every launch bracketed by CUDA events (averaged over `reps` cycles): a text table, one line per launch,
+// "level what rows nnz us algorithmic_MB GB/s"
+template <typename DType>
+int Subdomain<DType>::profile_vcycle(int reps, char *text, int cap)
+{
+    if (amg_fem.num_levels() < 1 || reps < 1) return -1;
+    std::vector<std::vector<amg::Hierarchy::ProfileRec>> runs(reps);
+    amg_fem.vcycle(num_vcycles); // warm
+    for (int r = 0; r < reps; r++)
+    {
+        amg_fem.prof = &runs[r];
+        amg_fem.vcycle(num_vcycles);
+        amg_fem.prof = nullptr;
+    }
+    dev::check(cudaStreamSynchronize(st()), "profile_vcycle");
+    std::string out;
+    char line[256];
+    double total_us = 0.0, total_bytes = 0.0;
+    for (size_t k = 0; k < runs[0].size(); k++)
+    {
+        double us = 0.0;
+        for (int r = 0; r < reps; r++)
+        {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, runs[r][k].e0, runs[r][k].e1);
+            us += 1e3 * ms / reps;
+        }
+        const auto &R = runs[0][k];
+        snprintf(line, sizeof(line), "%d %-34s %9d %10d %8.2f %8.2f %8.1f\n", R.level, R.what, R.rows, R.nnz, us, R.bytes / 1e6, us > 0 ? R.bytes / us / 1e3 : 0.0);
+        out += line;
+        total_us += us;
+        total_bytes += R.bytes;
+    }
+    snprintf(line, sizeof(line), "total: %zu launches, %.1f us (event-bracketed), %.1f MB algorithmic, %.1f GB/s\n", runs[0].size(), total_us, total_bytes / 1e6, total_bytes / total_us / 1e3);
+    out += line;
+    for (auto &run : runs)
+        for (auto &R : run) { cudaEventDestroy(R.e0); cudaEventDestroy(R.e1); }
+    if ((int)out.size() + 1 > cap) return -(int)out.size() - 1;
+    memcpy(text, out.c_str(), out.size() + 1);
     return 0;
 }
 

@@ -290,7 +290,13 @@ int prfdd_scatter_assign(double *dst, const double *buf, const int *idx, int cou
 }
 
 // lanes per row from the average row length (measured on B200, profiles/r1_spmv_tpr.txt and r1_notes.txt)
-static int lanes_per_row(double avg, int num_rows) { return avg <= 10 ? 1 : avg <= 18 ? 2 : (avg > 60 && num_rows < 50000) ? 16 : 8; }
+// 17.8 entries/row (level 1 of the 2-rank composite hierarchy): 8 lanes x 2 rows beats 2 lanes (2-GPU solve 25.9 -> 25.1 ms), hence 14
+static int lanes_per_row(double avg, int num_rows)
+{
+    static const double t1 = getenv("PRFDD_SPMV_T1") ? atof(getenv("PRFDD_SPMV_T1")) : 10.0; // experiment knobs
+    static const double t2 = getenv("PRFDD_SPMV_T2") ? atof(getenv("PRFDD_SPMV_T2")) : 14.0;
+    return avg <= t1 ? 1 : avg <= t2 ? 2 : (avg > 60 && num_rows < 50000) ? 16 : 8;
+}
 
 int prfdd_csr_plan(prfdd_csr_matrix *A, const int *ptr_host, int *long_rows_host, int capacity)
 {
