@@ -121,8 +121,9 @@ def golden_record(nel, ranks, eps, coarsening):
     return None
 
 
-def parity_block(hist, nel, ranks, eps, coarsening, rel_error):
+def parity_block(hist, nel, ranks, eps, coarsening, rel_error, precision="double"):
     rec = golden_record(nel, ranks, eps, coarsening)
+    rtol = HISTORY_RTOL if precision == "double" else 1.0e-4      # FP32 V-cycle: the history follows the FP64 oracle's to FP32 accuracy
     out = {"checked": False, "iterations": len(hist) - 1, "rel_error_vs_exact": rel_error, "history": [float(h) for h in hist]}
     # the manufactured solution is known: the converged iterate must be within the solve tolerance's reach of it at every size
     out["exact_solution_ok"] = bool(rel_error is not None and rel_error < 1.0e-6)
@@ -137,8 +138,8 @@ def parity_block(hist, nel, ranks, eps, coarsening, rel_error):
     out["iterations_oracle"] = len(gh) - 1
     same_len = len(gh) == len(hist)
     out["history_max_rel_diff"] = float(np.max(np.abs(np.array(hist) - gh) / gh)) if same_len else None
-    out["history_rtol"] = HISTORY_RTOL
-    out["ok"] = bool(same_len and out["history_max_rel_diff"] <= HISTORY_RTOL and out["exact_solution_ok"])
+    out["history_rtol"] = rtol
+    out["ok"] = bool(same_len and out["history_max_rel_diff"] <= rtol and out["exact_solution_ok"])
     return out
 
 
@@ -342,6 +343,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eps", type=float, default=0.0, help="mesh deformation (the reference's profiling meshes are Kershaw eps = 0.3, profile.sh:5-11)")
     ap.add_argument("--coarsening", default="hmis", choices=["hmis", "pmis"])
+    ap.add_argument("--amg-precision", default="double", choices=["double", "float"], help="float: the FP32 V-cycle (`Float float`, AMG/config.hpp:4; SURVEY 8f N3); the headline runs double")
     ap.add_argument("--phases", action="store_true", help="add the fenced per-phase table (reference Timer keys) of one extra solve")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -393,7 +395,7 @@ def main():
 
     stream = torch.cuda.Stream()
     S = pr.Solver(mesh_dir, stream=stream.cuda_stream, poly_degree=N_DEG, poly_reduction=REDUCTION, use_preconditioner=use_pc,
-                  outer_tolerance=TOL, proc_id=rank, num_procs=world, nccl_unique_id=uid, amg_coarsening=0 if args.coarsening == "pmis" else 1)
+                  outer_tolerance=TOL, proc_id=rank, num_procs=world, nccl_unique_id=uid, amg_coarsening=0 if args.coarsening == "pmis" else 1, amg_precision=1 if args.amg_precision == "float" else 0)
     S.setup_problem(4)
     stream.synchronize()
     setup_s = time.perf_counter() - t_setup0
@@ -511,13 +513,13 @@ def main():
                         "(level 0: %d rows, %d nnz; level 1: %d rows, %d nnz) -- the SpMV family is the dominant kernel of the solve (profiles/)" % (o[2], o[3], o[4], o[5]),
                         "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic(o),
                         "peak_source": roof_op["peak_source"], "avg_launch_ms": o[0], "algorithmic_bytes_per_launch": o[1],
-                        "algorithmic_bytes": "12 B per entry (col 4 + val 8) + 4 B per row pointer + 32 B per row (t_in, ds, r read, t_out written)"}
+                        "algorithmic_bytes": "12 B per entry (col 4 + val 8) + 4 B per row pointer + 32 B per row (t_in, ds, r read, t_out written); FP32 V-cycle: 8 B per entry, 16 B per row"}
         # whole solve: sum of the algorithmic bytes of every kernel launched in the timed region (each launcher reports its own:
         # prfdd_algorithmic_bytes) over the device time, per GPU
         per_gpu_gbs = alg_bytes / world / (ms * 1e-3) / 1e9
         whole = {"bound": "hbm", "algorithmic_bytes_per_solve": alg_bytes / args.steps, "achieved": per_gpu_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s per GPU",
                  "frac": per_gpu_gbs / peaks["hbm_gbs"], "note": "sum over all kernels of a solve of each kernel's algorithmic bytes (SURVEY 8d) / solve time / peak"}
-        parity = parity_block(hist, nel, world, args.eps, args.coarsening, err) if use_pc else {"checked": False, "ok": True, "why_unchecked": "no preconditioner"}
+        parity = parity_block(hist, nel, world, args.eps, args.coarsening, err, args.amg_precision) if use_pc else {"checked": False, "ok": True, "why_unchecked": "no preconditioner"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(args.cpu_nel)
@@ -527,7 +529,7 @@ def main():
                            if use_pc else "3D SEM Poisson, %dx%dx%d hex box mesh, N=7, FP64, flexible CG WITHOUT the PR-FDD preconditioner (PRFDD_BENCH_NO_PC set)" % tuple(nel),
                            "tolerance": TOL, "global_nodes": nodes, "iterations_per_solve": iters // args.steps, "l2": "working set (geometry 96 MiB + vectors + AMG hierarchy) exceeds the 126 MB L2",
                            "partition": "%dx%dx%d blocks of %dx%dx%d elements" % (tuple(P3) + tuple(n // p for n, p in zip(nel, P3))), "mesh_deformation_eps": args.eps,
-                           "amg_coarsening": args.coarsening, "time_to_solution_ms": ms / args.steps, "setup_s": setup_s, "mesh_generation_s": mesh_s, "rel_error_vs_exact": err,
+                           "amg_coarsening": args.coarsening, "amg_precision": args.amg_precision, "time_to_solution_ms": ms / args.steps, "setup_s": setup_s, "mesh_generation_s": mesh_s, "rel_error_vs_exact": err,
                            "amg_level_rows_rank0": amg_rows, "amg_level_nnz_rank0": amg_nnz},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * P * world, "d2h_bytes_per_step": 8 * P * world, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_sem_operator": roof_op, "roofline_whole_solve": whole, "parity": parity}

@@ -212,6 +212,40 @@ int prfdd_csr_residual(double *v, const int *ptr, const int *col, const double *
 int prfdd_dense_solve(double *x, const double *Ainv, const double *b, int n, prfdd_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * FP32 V-cycle: the reference builds its AMG classes and its Subdomain in `Float`
+ * (AMG/config.hpp:4, config.hpp:19-20 PTYPE Float); with `Float float` the hierarchy, the smoother and the
+ * cycle vectors are single precision under the FP64 outer solve (the outer residual stays an FP64 quantity).
+ * Same kernels as above instantiated for float: float values, float vectors, float row sums.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct prfdd_csr_matrix_f32
+{
+    const int *ptr;
+    const int *col;
+    const float *val;
+    int num_rows;
+    int num_cols;
+    int num_nnz;
+    int threads_per_row;
+    const int *long_rows;
+    int num_long_rows;
+    int long_row_threshold;
+} prfdd_csr_matrix_f32;
+int prfdd_csrm_multiply_f32(float *Au, const prfdd_csr_matrix_f32 *A, const float *u, prfdd_stream_t stream);
+int prfdd_csrm_matvec_f32(float *y, const prfdd_csr_matrix_f32 *A, const float *x, float alpha, float beta, prfdd_stream_t stream);
+int prfdd_csrm_residual_f32(float *v, const prfdd_csr_matrix_f32 *A, const float *u, const float *f, prfdd_stream_t stream);
+int prfdd_csrm_cheby_residual_f32(float *r, float *t, const prfdd_csr_matrix_f32 *A, const float *u, const float *f, const float *ds,
+                                  float c_hi, prfdd_stream_t stream);
+int prfdd_csrm_restrict_cheby_residual_f32(float *f, float *r, float *t, const prfdd_csr_matrix_f32 *R, const float *v, const float *ds,
+                                           float c_hi, prfdd_stream_t stream);
+int prfdd_csrm_cheby_step_f32(float *u, float *t_out, const prfdd_csr_matrix_f32 *A, const float *t_in, const float *r, const float *ds,
+                              float c, int last, int u_is_zero, prfdd_stream_t stream);
+int prfdd_cheby_order1_f32(float *u, const float *r, const float *ds, float c, int u_is_zero, int size, prfdd_stream_t stream);
+int prfdd_dense_solve_f32(float *x, const float *Ainv, const float *b, int n, prfdd_stream_t stream);
+/* the casts at the cycle's boundary: copy_from_domain_data / copy_to_domain_data with EType != DType (subdomain.okl:268-282) */
+int prfdd_cast_f64_to_f32(float *dst, const double *src, int n, prfdd_stream_t stream);
+int prfdd_cast_f32_to_f64(double *dst, const float *src, int n, prfdd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * polynomial reduction (restriction along the degree ladder)
  * ------------------------------------------------------------------------------------------- */
 /* u_c = (J^T x J^T [x J^T]) u_f per element, all directions fused.  J is n_f x n_c row-major,
@@ -428,6 +462,7 @@ typedef struct prfdd_options
     int outer_num_vectors;    /* 20 (domain.hpp:113) */
     int verbose;              /* print the reference's "Iter ..." lines on rank 0 */
     int amg_coarsening;       /* -1 library default, 0 PMIS, 1 HMIS (HYPRE coarsen type 10, subdomain.tpp:1853) */
+    int amg_precision;        /* 0 FP64 (`Float double`, the reference's setting, AMG/config.hpp:4), 1 FP32 V-cycle (`Float float`) */
 } prfdd_options;
 
 void prfdd_options_default(prfdd_options *opt);

@@ -267,12 +267,13 @@ def cheby_coefs(lower, upper, order):
     return np.ascontiguousarray(p[:order])
 
 
-def _csr_arrays(M):
-    """int32 / float64 views of a scipy CSR matrix for the C kernels, converted once per matrix (not per call)"""
-    c = getattr(M, "_oracle_arrays", None)
+def _csr_arrays(M, dtype=np.float64):
+    """int32 / value-type views of a scipy CSR matrix for the C kernels, converted once per matrix (not per call)"""
+    key = "_oracle_arrays_%s" % np.dtype(dtype).name
+    c = getattr(M, key, None)
     if c is None:
-        c = (np.ascontiguousarray(M.indptr, dtype=np.int32), np.ascontiguousarray(M.indices, dtype=np.int32), np.ascontiguousarray(M.data, dtype=np.float64))
-        M._oracle_arrays = c
+        c = (np.ascontiguousarray(M.indptr, dtype=np.int32), np.ascontiguousarray(M.indices, dtype=np.int32), np.ascontiguousarray(M.data, dtype=dtype))
+        setattr(M, key, c)
     return c
 
 
@@ -283,7 +284,10 @@ class Level:
 class Hierarchy:
     """levels[l]: A, P (l -> l+1 interpolation, rows = fine), R = P^T, ds, coefs, cf."""
 
-    def __init__(self, A0, cheby_order=2, max_coarse=9, theta=0.25, pmax=4, max_levels=25, with_smoother=True):
+    def __init__(self, A0, cheby_order=2, max_coarse=9, theta=0.25, pmax=4, max_levels=25, with_smoother=True, dtype=np.float64):
+        # dtype float32: the reference's `Float float` (AMG/config.hpp:4) -- HYPRE's set-up stays double, the extraction into the
+        # amg:: classes casts matrices, ds and the Chebyshev coefficients to Float (subdomain.tpp:3491-3549), the cycle runs in Float
+        self.dtype = np.dtype(dtype).type
         self.levels = []
         A = A0.tocsr().astype(np.float64); A.sort_indices()
         l = 0
@@ -309,6 +313,11 @@ class Hierarchy:
         last = self.levels[-1]
         last.Ainv = np.linalg.inv(last.A.toarray()) if last.n > 0 else np.zeros((0, 0))
         self.cheby_order = cheby_order
+        if self.dtype is np.float32:
+            for L in self.levels:
+                if hasattr(L, "ds"):
+                    L.ds32 = L.ds.astype(np.float32)
+            last.Ainv32 = last.Ainv.astype(np.float32)
 
     @property
     def num_levels(self):
@@ -317,40 +326,45 @@ class Hierarchy:
     # ---- V-cycle: subdomain.tpp:4015-4139 (down leg, coarse solve, up leg) ------------------
     def _smooth(self, L, u, f, u_is_zero):
         """scaled_residual + polynomial_evaluation x (order-1) + update_field (subdomain.tpp:3652-3657), host branches."""
-        K = _c.lib()
+        f32 = self.dtype is np.float32
+        K = _c.lib32() if f32 else _c.lib()
+        cs = C.c_float if f32 else C.c_double
+        ds = L.ds32 if f32 else L.ds
         A = L.A
-        ptr, col, val = _csr_arrays(A)
+        ptr, col, val = _csr_arrays(A, self.dtype)
         n = L.n
-        r = np.zeros(n); w = np.zeros(n); v = np.zeros(n)
+        r = np.zeros(n, self.dtype); w = np.zeros(n, self.dtype); v = np.zeros(n, self.dtype)
         k = self.cheby_order
-        K.o_scaled_residual(P_(r), P_(w), P_(ptr), P_(col), P_(val), P_(u), P_(f), P_(L.ds), C.c_double(L.coefs[k - 1]), C.c_int(n))
+        K.o_scaled_residual(P_(r), P_(w), P_(ptr), P_(col), P_(val), P_(u), P_(f), P_(ds), cs(L.coefs[k - 1]), C.c_int(n))
         for pidx in range(k - 2, -1, -1):
-            K.o_polynomial_evaluation(P_(w), P_(v), P_(ptr), P_(col), P_(val), P_(r), P_(L.ds), C.c_double(L.coefs[pidx]), C.c_int(n))
-        K.o_update_field(P_(u), P_(w), P_(L.ds), C.c_int(n))
+            K.o_polynomial_evaluation(P_(w), P_(v), P_(ptr), P_(col), P_(val), P_(r), P_(ds), cs(L.coefs[pidx]), C.c_int(n))
+        K.o_update_field(P_(u), P_(w), P_(ds), C.c_int(n))
 
-    @staticmethod
-    def _matvec(M, y, x, alpha, beta):
-        K = _c.lib()
-        ptr, col, val = _csr_arrays(M)
-        K.o_amg_matvec(P_(y), P_(ptr), P_(col), P_(val), P_(x), C.c_double(alpha), C.c_double(beta), C.c_int(M.shape[0]))
+    def _matvec(self, M, y, x, alpha, beta):
+        f32 = self.dtype is np.float32
+        K = _c.lib32() if f32 else _c.lib()
+        cs = C.c_float if f32 else C.c_double
+        ptr, col, val = _csr_arrays(M, self.dtype)
+        K.o_amg_matvec(P_(y), P_(ptr), P_(col), P_(val), P_(x), cs(alpha), cs(beta), C.c_int(M.shape[0]))
 
     def vcycle(self, f0, num_vcycles=1):
         nl = self.num_levels
         f = [None] * nl; u = [None] * nl
-        f[0] = np.ascontiguousarray(f0, dtype=np.float64).copy()
-        u[0] = np.zeros(self.levels[0].n)
+        dt = self.dtype
+        f[0] = np.ascontiguousarray(f0, dtype=dt).copy()
+        u[0] = np.zeros(self.levels[0].n, dt)
         for _ in range(num_vcycles):
             for l in range(nl - 1):
                 L = self.levels[l]
                 if l > 0:
-                    u[l] = np.zeros(L.n)
+                    u[l] = np.zeros(L.n, dt)
                 self._smooth(L, u[l], f[l], True)
                 v = f[l].copy()
                 self._matvec(L.A, v, u[l], -1.0, 1.0)            # residual (tpp:3660-3661)
-                f[l + 1] = np.zeros(self.levels[l + 1].n)
+                f[l + 1] = np.zeros(self.levels[l + 1].n, dt)
                 self._matvec(L.R, f[l + 1], v, 1.0, 0.0)          # restrict (tpp:3666-3672)
             last = self.levels[-1]
-            u[nl - 1] = last.Ainv @ f[nl - 1]                     # hypre_GaussElimSolve (tpp:4084)
+            u[nl - 1] = (last.Ainv32 if dt is np.float32 else last.Ainv) @ f[nl - 1]   # hypre_GaussElimSolve (tpp:4084)
             for l in range(nl - 1, 0, -1):
                 L = self.levels[l - 1]
                 self._matvec(L.P, u[l - 1], u[l], 1.0, 1.0)       # coarse-grid correction (tpp:4098)

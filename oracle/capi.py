@@ -17,7 +17,7 @@ i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 def build():
     """Compile liboracle.so, liboracle_omp.so (and oracle/_ref when /root/reference is mounted)."""
-    subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so", "liboracle_omp.so"])
+    subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so", "liboracle_omp.so", "liboracle_f32.so"])
     if os.path.isdir("/root/reference"):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
 
@@ -49,6 +49,20 @@ def lib():
         _lib.oracle_hgll.restype = C.c_double
         _lib.o_serial_sum.restype = C.c_double
     return _lib
+
+
+_lib32 = None
+
+
+def lib32():
+    """the kernels compiled with DType = float (`Float float`, AMG/config.hpp:4): only the AMG loops are used from it"""
+    global _lib32
+    if _lib32 is None:
+        path = os.path.join(HERE, "liboracle_f32.so")
+        if not os.path.exists(path):
+            build()
+        _lib32 = C.CDLL(path)
+    return _lib32
 
 
 def ref(dim):

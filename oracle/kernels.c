@@ -41,7 +41,12 @@
 #endif
 
 #define BLOCK_SIZE 128
-typedef double DType;
+/* liboracle_f32.so is this file compiled with -DORACLE_DTYPE=float: the reference's `Float float` (AMG/config.hpp:4,
+ * config.hpp:19-20 PTYPE Float), used for the AMG smoother / matvec loops of the FP32 V-cycle */
+#ifndef ORACLE_DTYPE
+#define ORACLE_DTYPE double
+#endif
+typedef ORACLE_DTYPE DType;
 typedef double EType;
 
 /* ------------------------------------------------------------------ domain.okl */

@@ -284,7 +284,7 @@ class SubdomainWorld:
         if self.use_preconditioner:
             S.A_sub_fem = self._assemble_fem_conforming(S)
             S.A_fem = S.A_sub_fem                                                   # Q_int is the identity (tpp:3414-3472)
-            S.amg = _amg.Hierarchy(S.A_fem, cheby_order=self.cheby_order)
+            S.amg = _amg.Hierarchy(S.A_fem, cheby_order=self.cheby_order, dtype=np.float32 if getattr(self, "amg_precision", "double") == "float" else np.float64)
         self._alloc(S)
         return S
 

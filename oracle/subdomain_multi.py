@@ -412,7 +412,7 @@ def _build_rank(world, G, S):
         M.add_entries(rows, cols, vals)
         M.assemble()
         S.A_fem = M.to_scipy()
-        S.amg = _amg.Hierarchy(S.A_fem, cheby_order=world.cheby_order)
+        S.amg = _amg.Hierarchy(S.A_fem, cheby_order=world.cheby_order, dtype=np.float32 if getattr(world, "amg_precision", "double") == "float" else np.float64)
 
 
 def _matching(dim, R, ki, kj, kind, idx):

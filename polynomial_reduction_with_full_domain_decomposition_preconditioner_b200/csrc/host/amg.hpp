@@ -661,26 +661,65 @@ inline std::vector<double> dense_inverse(const HostCSR &A)
     return I;
 }
 
+// overloads that pick the FP64 / FP32 instance of a kernel from the pointer type, so that the cycle below is written once
+namespace k
+{
+inline int cheby_residual(double *r, double *t, const prfdd_csr_matrix *A, const prfdd_csr_matrix_f32 *, const double *u, const double *f, const double *ds, double c, cudaStream_t st) { return prfdd_csrm_cheby_residual(r, t, A, u, f, ds, c, st); }
+inline int cheby_residual(float *r, float *t, const prfdd_csr_matrix *, const prfdd_csr_matrix_f32 *A, const float *u, const float *f, const float *ds, double c, cudaStream_t st) { return prfdd_csrm_cheby_residual_f32(r, t, A, u, f, ds, (float)c, st); }
+inline int cheby_step(double *u, double *to, const prfdd_csr_matrix *A, const prfdd_csr_matrix_f32 *, const double *ti, const double *r, const double *ds, double c, int last, int zero, cudaStream_t st) { return prfdd_csrm_cheby_step(u, to, A, ti, r, ds, c, last, zero, st); }
+inline int cheby_step(float *u, float *to, const prfdd_csr_matrix *, const prfdd_csr_matrix_f32 *A, const float *ti, const float *r, const float *ds, double c, int last, int zero, cudaStream_t st) { return prfdd_csrm_cheby_step_f32(u, to, A, ti, r, ds, (float)c, last, zero, st); }
+inline int cheby_order1(double *u, const double *r, const double *ds, double c, int zero, int n, cudaStream_t st) { return prfdd_cheby_order1(u, r, ds, c, zero, n, st); }
+inline int cheby_order1(float *u, const float *r, const float *ds, double c, int zero, int n, cudaStream_t st) { return prfdd_cheby_order1_f32(u, r, ds, (float)c, zero, n, st); }
+inline int residual(double *v, const prfdd_csr_matrix *A, const prfdd_csr_matrix_f32 *, const double *u, const double *f, cudaStream_t st) { return prfdd_csrm_residual(v, A, u, f, st); }
+inline int residual(float *v, const prfdd_csr_matrix *, const prfdd_csr_matrix_f32 *A, const float *u, const float *f, cudaStream_t st) { return prfdd_csrm_residual_f32(v, A, u, f, st); }
+inline int restrict_head(double *f, double *r, double *t, const prfdd_csr_matrix *R, const prfdd_csr_matrix_f32 *, const double *v, const double *ds, double c, cudaStream_t st) { return prfdd_csrm_restrict_cheby_residual(f, r, t, R, v, ds, c, st); }
+inline int restrict_head(float *f, float *r, float *t, const prfdd_csr_matrix *, const prfdd_csr_matrix_f32 *R, const float *v, const float *ds, double c, cudaStream_t st) { return prfdd_csrm_restrict_cheby_residual_f32(f, r, t, R, v, ds, (float)c, st); }
+inline int multiply(double *y, const prfdd_csr_matrix *A, const prfdd_csr_matrix_f32 *, const double *x, cudaStream_t st) { return prfdd_csrm_multiply(y, A, x, st); }
+inline int multiply(float *y, const prfdd_csr_matrix *, const prfdd_csr_matrix_f32 *A, const float *x, cudaStream_t st) { return prfdd_csrm_multiply_f32(y, A, x, st); }
+inline int add_product(double *y, const prfdd_csr_matrix *A, const prfdd_csr_matrix_f32 *, const double *x, cudaStream_t st) { return prfdd_csrm_matvec(y, A, x, 1.0, 1.0, st); }
+inline int add_product(float *y, const prfdd_csr_matrix *, const prfdd_csr_matrix_f32 *A, const float *x, cudaStream_t st) { return prfdd_csrm_matvec_f32(y, A, x, 1.0f, 1.0f, st); }
+inline int dense(double *x, const double *M, const double *b, int n, cudaStream_t st) { return prfdd_dense_solve(x, M, b, n, st); }
+inline int dense(float *x, const float *M, const float *b, int n, cudaStream_t st) { return prfdd_dense_solve_f32(x, M, b, n, st); }
+} // namespace k
+
 struct DeviceCSR
 {
     int num_rows = 0, num_cols = 0, nnz = 0, tpr = 4;
     dev::memory ptr, col, val, long_rows;
-    prfdd_csr_matrix desc = {}; // device arrays + launch plan, as the C ABI takes them
-    void upload(const HostCSR &A)
+    prfdd_csr_matrix desc = {};       // device arrays + launch plan, as the C ABI takes them (FP64 values)
+    prfdd_csr_matrix_f32 desc32 = {}; // the same with FP32 values (fp32 upload)
+    void upload(const HostCSR &A, bool fp32 = false)
     {
         num_rows = A.num_rows; num_cols = A.num_cols; nnz = A.nnz();
         ptr = prfdd_host::device.malloc<int>(num_rows + 1);
         col = prfdd_host::device.malloc<int>(std::max(nnz, 1));
-        val = prfdd_host::device.malloc<double>(std::max(nnz, 1));
         ptr.copyFrom(A.ptr.data(), (num_rows + 1) * sizeof(int));
         col.copyFrom(A.col.data(), nnz * sizeof(int));
-        val.copyFrom(A.val.data(), nnz * sizeof(double));
         desc = prfdd_csr_matrix();
-        desc.ptr = ptr.as<int>(); desc.col = col.as<int>(); desc.val = val.as<double>();
+        desc.ptr = ptr.as<int>(); desc.col = col.as<int>();
         desc.num_rows = num_rows;
         desc.num_cols = num_cols;
+        if (fp32)
+        {
+            // HYPRE computes in double either way; the extraction into the amg:: classes casts to Float (subdomain.tpp:3491-3549)
+            std::vector<float> v32(A.val.begin(), A.val.end());
+            val = prfdd_host::device.malloc<float>(std::max(nnz, 1));
+            val.copyFrom(v32.data(), nnz * sizeof(float));
+            desc.val = reinterpret_cast<const double *>(val.ptr()); // only non-NULL-ness is used by the planner
+        }
+        else
+        {
+            val = prfdd_host::device.malloc<double>(std::max(nnz, 1));
+            val.copyFrom(A.val.data(), nnz * sizeof(double));
+            desc.val = val.as<double>();
+        }
         long_rows = ::plan_csr(desc, A.ptr.data());
         tpr = desc.threads_per_row;
+        desc32 = prfdd_csr_matrix_f32();
+        desc32.ptr = desc.ptr; desc32.col = desc.col; desc32.val = fp32 ? val.as<float>() : nullptr;
+        desc32.num_rows = num_rows; desc32.num_cols = num_cols; desc32.num_nnz = desc.num_nnz; desc32.threads_per_row = desc.threads_per_row;
+        desc32.long_rows = desc.long_rows; desc32.num_long_rows = desc.num_long_rows; desc32.long_row_threshold = desc.long_row_threshold;
+        if (fp32) { desc.val = nullptr; desc.col = nullptr; } // no FP64 values exist: an FP64 call on this matrix fails loudly (-8)
     }
 };
 
@@ -701,6 +740,7 @@ class Hierarchy
     std::vector<Level> levels;
     int cheby_order = 2;
     int coarsening = -1; // COARSEN_PMIS / COARSEN_HMIS; -1: PRFDD_AMG_COARSENING or the default
+    bool fp32 = false;   // FP32 matrices, vectors and cycle (`Float float`, AMG/config.hpp:4); the set-up is FP64 either way
     std::vector<double> Ainv_hst;
     dev::memory Ainv;
     // Collapsed coarse levels.  Below the first level the V-cycle always starts from a zero guess and the Chebyshev coefficients are
@@ -778,28 +818,42 @@ class Hierarchy
         if (on_device) upload();
     }
 
-    void upload()
+    template <typename T>
+    static dev::memory upload_vector(const std::vector<double> &h, size_t count)
+    {
+        std::vector<T> t(h.begin(), h.begin() + count);
+        dev::memory m = prfdd_host::device.malloc<T>(std::max<size_t>(count, 1));
+        m.copyFrom(t.data(), count * sizeof(T));
+        return m;
+    }
+
+    template <typename T>
+    void upload_t()
     {
         using prfdd_host::device;
         for (auto &L : levels)
         {
-            L.dA.upload(L.A);
-            if (L.P.num_rows > 0) { L.dP.upload(L.P); L.dR.upload(L.R); }
+            L.dA.upload(L.A, fp32);
+            if (L.P.num_rows > 0) { L.dP.upload(L.P, fp32); L.dR.upload(L.R, fp32); }
             const int n = std::max(L.n, 1);
-            L.ds = device.malloc<double>(n);
-            L.ds.copyFrom(L.ds_hst.data(), L.n * sizeof(double));
-            L.f = device.malloc<double>(n); L.u = device.malloc<double>(n); L.r = device.malloc<double>(n);
-            L.t0 = device.malloc<double>(n); L.t1 = device.malloc<double>(n); L.v = device.malloc<double>(n);
+            L.ds = upload_vector<T>(L.ds_hst, (size_t)L.n);
+            L.f = device.malloc<T>(n); L.u = device.malloc<T>(n); L.r = device.malloc<T>(n);
+            L.t0 = device.malloc<T>(n); L.t1 = device.malloc<T>(n); L.v = device.malloc<T>(n);
         }
-        Ainv = device.malloc<double>(std::max<size_t>(Ainv_hst.size(), 1));
-        Ainv.copyFrom(Ainv_hst.data(), Ainv_hst.size() * sizeof(double));
+        Ainv = upload_vector<T>(Ainv_hst, Ainv_hst.size());
         setup_mark("  AMG: upload");
         static const bool no_collapse = getenv("PRFDD_AMG_NO_COLLAPSE") != nullptr;
-        if (!no_collapse) collapse(4096);
+        if (!no_collapse) collapse_t<T>(4096);
         setup_mark("  AMG: collapsed coarse levels");
     }
+    void upload()
+    {
+        if (fp32) upload_t<float>();
+        else upload_t<double>();
+    }
 
-    void collapse(int max_rows)
+    template <typename T>
+    void collapse_t(int max_rows)
     {
         using prfdd_host::device;
         const int nl = num_levels();
@@ -811,43 +865,44 @@ class Hierarchy
         cudaStream_t st = device.stream;
         Level &L = levels[lc];
         const size_t n = (size_t)L.n;
-        dev::memory Bt = device.malloc<double>(n * n); // row i = sub-cycle applied to e_i = column i of B
-        const double one = 1.0;
+        dev::memory Bt = device.malloc<T>(n * n); // row i = sub-cycle applied to e_i = column i of B
+        const T one = (T)1;
         for (size_t i = 0; i < n; i++)
         {
-            cudaMemsetAsync(L.f.as<double>(), 0, n * sizeof(double), st);
-            cudaMemcpyAsync(L.f.as<double>() + i, &one, sizeof(double), cudaMemcpyHostToDevice, st);
-            cycle_from(lc);
-            cudaMemcpyAsync(Bt.as<double>() + i * n, L.u.as<double>(), n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+            cudaMemsetAsync(L.f.as<T>(), 0, n * sizeof(T), st);
+            cudaMemcpyAsync(L.f.as<T>() + i, &one, sizeof(T), cudaMemcpyHostToDevice, st);
+            cycle_from_t<T>(lc, true, false);
+            cudaMemcpyAsync(Bt.as<T>() + i * n, L.u.as<T>(), n * sizeof(T), cudaMemcpyDeviceToDevice, st);
         }
-        std::vector<double> bt(n * n), b(n * n);
-        Bt.copyTo(bt.data(), n * n * sizeof(double));
+        std::vector<T> bt(n * n), b(n * n);
+        Bt.copyTo(bt.data(), n * n * sizeof(T));
         for (size_t i = 0; i < n; i++)
             for (size_t j = 0; j < n; j++) b[j * n + i] = bt[i * n + j];
-        Bdense = device.malloc<double>(n * n);
-        Bdense.copyFrom(b.data(), n * n * sizeof(double));
+        Bdense = device.malloc<T>(n * n);
+        Bdense.copyFrom(b.data(), n * n * sizeof(T));
         collapse_level = lc;
     }
 
     // hypre-style Chebyshev smoothing: r = ds(f - A u); w = c[k-1] r; for p = k-2..0: w = c[p] r + ds A ds w; u += ds w
-    void smooth(Level &L, bool u_is_zero, bool residual_done = false)
+    template <typename T>
+    void smooth_t(Level &L, bool u_is_zero, bool residual_done)
     {
         const int lv = (int)(&L - levels.data());
         cudaStream_t st = prfdd_host::device.stream;
         const int k = cheby_order;
-        double *u = L.u.as<double>(), *r = L.r.as<double>(), *t0 = L.t0.as<double>(), *t1 = L.t1.as<double>();
-        const double *ds = L.ds.as<double>(), *f = L.f.as<double>();
+        T *u = L.u.as<T>(), *r = L.r.as<T>(), *t0 = L.t0.as<T>(), *t1 = L.t1.as<T>();
+        const T *ds = L.ds.as<T>(), *f = L.f.as<T>();
         // residual_done: the restriction that produced f already wrote r and t0 (prfdd_restrict_cheby_residual)
-        if (!residual_done) timed(lv, u_is_zero ? "cheby_residual(u=0)" : "cheby_residual", L.n, L.dA.nnz, [&] { return prfdd_csrm_cheby_residual(r, t0, &L.dA.desc, u_is_zero ? nullptr : u, f, ds, L.coefs[k - 1], st); });
+        if (!residual_done) timed(lv, u_is_zero ? "cheby_residual(u=0)" : "cheby_residual", L.n, L.dA.nnz, [&] { return k::cheby_residual(r, t0, &L.dA.desc, &L.dA.desc32, u_is_zero ? (const T *)nullptr : u, f, ds, L.coefs[k - 1], st); });
         if (k == 1)
         {
-            timed(lv, "cheby_order1", L.n, 0, [&] { return prfdd_cheby_order1(u, r, ds, L.coefs[0], u_is_zero ? 1 : 0, L.n, st); });
+            timed(lv, "cheby_order1", L.n, 0, [&] { return k::cheby_order1(u, r, ds, L.coefs[0], u_is_zero ? 1 : 0, L.n, st); });
             return;
         }
-        double *tin = t0, *tout = t1;
+        T *tin = t0, *tout = t1;
         for (int p = k - 2; p >= 0; p--)
         {
-            timed(lv, "cheby_step", L.n, L.dA.nnz, [&] { return prfdd_csrm_cheby_step(u, tout, &L.dA.desc, tin, r, ds, L.coefs[p], p == 0 ? 1 : 0, u_is_zero ? 1 : 0, st); });
+            timed(lv, "cheby_step", L.n, L.dA.nnz, [&] { return k::cheby_step(u, tout, &L.dA.desc, &L.dA.desc32, tin, r, ds, L.coefs[p], p == 0 ? 1 : 0, u_is_zero ? 1 : 0, st); });
             std::swap(tin, tout);
         }
     }
@@ -855,7 +910,8 @@ class Hierarchy
     // zero-guess cycle over the levels l0 .. coarsest: levels[l0].f -> levels[l0].u   (subdomain.tpp:4012-4139)
     // head_done: the caller produced levels[l0].f with a product that also wrote the zero-guess head r = ds f, t0 = ds (c r)
     // (prfdd_csrm_restrict_cheby_residual), so the first smoothing skips it
-    void cycle_from(int l0, bool first_guess_is_zero = true, bool head_done = false)
+    template <typename T>
+    void cycle_from_t(int l0, bool first_guess_is_zero, bool head_done)
     {
         cudaStream_t st = prfdd_host::device.stream;
         const int nl = num_levels();
@@ -863,25 +919,29 @@ class Hierarchy
         for (int l = l0; l < bottom; l++)
         {
             Level &L = levels[l];
-            smooth(L, l > l0 || first_guess_is_zero, l > l0 || (head_done && first_guess_is_zero));
-            timed(l, "csr_residual", L.n, L.dA.nnz, [&] { return prfdd_csrm_residual(L.v.as<double>(), &L.dA.desc, L.u.as<double>(), L.f.as<double>(), st); });
+            smooth_t<T>(L, l > l0 || first_guess_is_zero, l > l0 || (head_done && first_guess_is_zero));
+            timed(l, "csr_residual", L.n, L.dA.nnz, [&] { return k::residual(L.v.as<T>(), &L.dA.desc, &L.dA.desc32, L.u.as<T>(), L.f.as<T>(), st); });
             Level &Lc = levels[l + 1];
             if (l + 1 < bottom) // the coarse level is smoothed next: fuse the head of that smoothing into the restriction
-                timed(l, "restrict+cheby_residual", Lc.n, L.dR.nnz, [&] { return prfdd_csrm_restrict_cheby_residual(Lc.f.as<double>(), Lc.r.as<double>(), Lc.t0.as<double>(), &L.dR.desc, L.v.as<double>(),
-                                                                 Lc.ds.as<double>(), Lc.coefs[cheby_order - 1], st); });
+                timed(l, "restrict+cheby_residual", Lc.n, L.dR.nnz, [&] { return k::restrict_head(Lc.f.as<T>(), Lc.r.as<T>(), Lc.t0.as<T>(), &L.dR.desc, &L.dR.desc32, L.v.as<T>(), Lc.ds.as<T>(), Lc.coefs[cheby_order - 1], st); });
             else
-                timed(l, "restrict", Lc.n, L.dR.nnz, [&] { return prfdd_csrm_multiply(Lc.f.as<double>(), &L.dR.desc, L.v.as<double>(), st); });
+                timed(l, "restrict", Lc.n, L.dR.nnz, [&] { return k::multiply(Lc.f.as<T>(), &L.dR.desc, &L.dR.desc32, L.v.as<T>(), st); });
         }
         Level &last = levels[bottom];
-        if (bottom == nl - 1) timed(bottom, "dense_solve", last.n, 0, [&] { return prfdd_dense_solve(last.u.as<double>(), Ainv.as<double>(), last.f.as<double>(), last.n, st); });
-        else timed(bottom, "collapsed coarse levels (dense)", last.n, 0, [&] { return prfdd_dense_solve(last.u.as<double>(), Bdense.as<double>(), last.f.as<double>(), last.n, st); });
+        if (bottom == nl - 1) timed(bottom, "dense_solve", last.n, 0, [&] { return k::dense(last.u.as<T>(), Ainv.as<T>(), last.f.as<T>(), last.n, st); });
+        else timed(bottom, "collapsed coarse levels (dense)", last.n, 0, [&] { return k::dense(last.u.as<T>(), Bdense.as<T>(), last.f.as<T>(), last.n, st); });
         for (int l = bottom; l > l0; l--)
         {
             Level &L = levels[l - 1];
             Level &Lc = levels[l];
-            timed(l - 1, "prolong", L.n, L.dP.nnz, [&] { return prfdd_csrm_matvec(L.u.as<double>(), &L.dP.desc, Lc.u.as<double>(), 1.0, 1.0, st); });
-            smooth(L, false);
+            timed(l - 1, "prolong", L.n, L.dP.nnz, [&] { return k::add_product(L.u.as<T>(), &L.dP.desc, &L.dP.desc32, Lc.u.as<T>(), st); });
+            smooth_t<T>(L, false, false);
         }
+    }
+    void cycle_from(int l0, bool first_guess_is_zero = true, bool head_done = false)
+    {
+        if (fp32) cycle_from_t<float>(l0, first_guess_is_zero, head_done);
+        else cycle_from_t<double>(l0, first_guess_is_zero, head_done);
     }
 
     // levels[0].f holds the right-hand side; result in levels[0].u

@@ -93,6 +93,7 @@ void prfdd_options_default(prfdd_options *o)
     o->outer_num_vectors = 20;
     o->verbose = 0;
     o->amg_coarsening = -1;
+    o->amg_precision = 0;
 }
 
 int prfdd_solver_create(prfdd_solver **out, const char *directory, const prfdd_options *opt, prfdd_stream_t stream)

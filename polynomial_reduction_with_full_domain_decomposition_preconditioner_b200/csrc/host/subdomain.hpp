@@ -477,6 +477,7 @@ void Subdomain<DType>::build_single_rank(std::map<int, std::unique_ptr<Domain<DT
         assemble_low_order_fem();
         setup_mark("low-order FEM assembly");
         amg_fem.coarsening = opt.amg_coarsening;
+        amg_fem.fp32 = opt.amg_precision == 1;
         amg_fem.setup(A_fem_hst, cheby_order);
         setup_mark("AMG #2 (hierarchy, upload, collapsed coarse levels)");
     }
@@ -926,6 +927,23 @@ void Subdomain<DType>::low_order_preconditioner(const memory &z, const memory &r
     if (interface_is_identity)
     {
         // Qt_int / Q_int are identities: assemble straight into the V-cycle's right-hand side, scatter straight out of its solution
+        if (amg_fem.fp32)
+        {
+            // FP32 cycle under the FP64 Krylov method: cast in, cycle, cast out (copy_from/to_domain_data with EType != DType)
+            const memory *src = r_assembled;
+            if (!src)
+            {
+                subdomain_operator.Qt.multiply(work_dev[0], r_sub);
+                src = &work_dev[0];
+            }
+            dev::check_rc(prfdd_cast_f64_to_f32(L0.f.as<float>(), dp(*src), L0.n, st()), "cast to FP32");
+            timer.start("subdomain.preconditioner.down_leg_gpu");
+            amg_fem.vcycle(num_vcycles);
+            timer.stop("subdomain.preconditioner.down_leg_gpu");
+            dev::check_rc(prfdd_cast_f32_to_f64(dp(work_dev[0]), L0.u.as<float>(), L0.n, st()), "cast to FP64");
+            subdomain_operator.Q.multiply(z_sub, work_dev[0]);
+            return;
+        }
         memory f_own = L0.f;
         if (r_assembled)
             L0.f = r_assembled->slice(0, L0.n); // the cycle reads its right-hand side in place
@@ -953,8 +971,13 @@ void Subdomain<DType>::low_order_preconditioner(const memory &z, const memory &r
     }
     // interface assembly fused with the head of level 0's zero-guess smoothing: f = Qt_int a, r = ds f, t0 = ds (c r) in one pass
     timer.start("subdomain.preconditioner.assemble_composite");
-    const bool head = amg_fem.num_levels() > 1 && Qt_int.num_rows == L0.n && Qt_int.num_nnz > 0 && !Qt_int.unit_values;
-    if (head)
+    const bool head = !amg_fem.fp32 && amg_fem.num_levels() > 1 && Qt_int.num_rows == L0.n && Qt_int.num_nnz > 0 && !Qt_int.unit_values;
+    if (amg_fem.fp32)
+    {
+        Qt_int.multiply(work_dev[1], r_assembled ? *r_assembled : work_dev[0]);
+        dev::check_rc(prfdd_cast_f64_to_f32(L0.f.as<float>(), dp(work_dev[1]), L0.n, st()), "cast to FP32");
+    }
+    else if (head)
         dev::check_rc(prfdd_csrm_restrict_cheby_residual(dp(L0.f), dp(L0.r), dp(L0.t0), &Qt_int.desc, dp(r_assembled ? *r_assembled : work_dev[0]), dp(L0.ds),
                                                          L0.coefs[amg_fem.cheby_order - 1], st()), "Qt_int + smoothing head");
     else
@@ -964,7 +987,13 @@ void Subdomain<DType>::low_order_preconditioner(const memory &z, const memory &r
     amg_fem.vcycle(num_vcycles, head);
     timer.stop("subdomain.preconditioner.down_leg_gpu");
     timer.start("subdomain.preconditioner.unassemble_composite");
-    Q_int.multiply(work_dev[0], L0.u);
+    if (amg_fem.fp32)
+    {
+        dev::check_rc(prfdd_cast_f32_to_f64(dp(work_dev[1]), L0.u.as<float>(), L0.n, st()), "cast to FP64");
+        Q_int.multiply(work_dev[0], work_dev[1]);
+    }
+    else
+        Q_int.multiply(work_dev[0], L0.u);
     timer.stop("subdomain.preconditioner.unassemble_composite");
     timer.start("subdomain.preconditioner.unassemble_subdomain");
     subdomain_operator.Q.multiply(z_sub, work_dev[0]);
@@ -1321,6 +1350,15 @@ int Subdomain<DType>::apply(int what, const double *in_host, double *out_host)
     }
     case PRFDD_APPLY_VCYCLE:
     {
+        if (amg_fem.fp32)
+        {
+            work_dev[0].copyFrom(in_host, num_dofs * sizeof(double));
+            dev::check_rc(prfdd_cast_f64_to_f32(amg_fem.levels[0].f.template as<float>(), dp(work_dev[0]), num_dofs, st()), "cast to FP32");
+            amg_fem.vcycle(num_vcycles);
+            dev::check_rc(prfdd_cast_f32_to_f64(dp(work_dev[0]), amg_fem.levels[0].u.template as<float>(), num_dofs, st()), "cast to FP64");
+            work_dev[0].copyTo(out_host, num_dofs * sizeof(double));
+            return 0;
+        }
         amg_fem.levels[0].f.copyFrom(in_host, num_dofs * sizeof(double));
         amg_fem.vcycle(num_vcycles);
         amg_fem.levels[0].u.copyTo(out_host, num_dofs * sizeof(double));
@@ -1347,7 +1385,9 @@ int Subdomain<DType>::time_spmv(int reps, double out[6])
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
+    const bool f32 = amg_fem.fp32;
     auto step = [&](amg::Level &L) {
+        if (f32) return prfdd_csrm_cheby_step_f32(L.u.as<float>(), L.t1.as<float>(), &L.dA.desc32, L.t0.as<float>(), L.r.as<float>(), L.ds.as<float>(), (float)L.coefs[0], 0, 0, stream);
         return prfdd_csrm_cheby_step(L.u.as<double>(), L.t1.as<double>(), &L.dA.desc, L.t0.as<double>(), L.r.as<double>(), L.ds.as<double>(), L.coefs[0], 0, 0, stream);
     };
     for (int w = 0; w < 4; w++) { step(amg_fem.levels[0]); step(amg_fem.levels[1]); }
@@ -1367,7 +1407,8 @@ int Subdomain<DType>::time_spmv(int reps, double out[6])
     for (int l = 0; l < 2; l++)
     {
         const amg::Level &L = amg_fem.levels[l];
-        bytes += 0.5 * (12.0 * L.A.nnz() + 4.0 * (L.n + 1) + 32.0 * L.n); // col 4 + val 8 per entry; ptr; t_in, ds, r read and t_out written once per row
+        const double vb = f32 ? 4.0 : 8.0;
+        bytes += 0.5 * ((4.0 + vb) * L.A.nnz() + 4.0 * (L.n + 1) + 4.0 * vb * L.n); // col + val per entry; ptr; t_in, ds, r read and t_out written once per row
         out[2 + 2 * l] = L.n;
         out[3 + 2 * l] = L.A.nnz();
     }

@@ -429,6 +429,7 @@ void Subdomain<DType>::build_multi_rank(std::map<int, std::unique_ptr<Domain<DTy
         assemble_low_order_fem();
         setup_mark("low-order FEM assembly");
         amg_fem.coarsening = opt.amg_coarsening;
+        amg_fem.fp32 = opt.amg_precision == 1;
         amg_fem.setup(A_fem_hst, cheby_order);
         setup_mark("AMG #2 (hierarchy, upload, collapsed coarse levels)");
     }

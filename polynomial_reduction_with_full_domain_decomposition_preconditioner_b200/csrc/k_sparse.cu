@@ -23,8 +23,9 @@ constexpr int kSpThreads = 256;
 // shuffles are always executed by the whole warp.  RPG > 1: every sub-warp walks RPG rows at once
 // (rows r, r + 32/TPR, ...), which multiplies the independent col/val -> x load chains a lane has in
 // flight; the long rows of the coarse AMG levels are latency bound without it.
-template <int TPR, int RPG, bool UNIT, class Epi>
-__global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, int row_start, int num_rows, int skip_len, Epi epi)
+// VT: value type of the matrix, the gathered vector and the row sums (double; float for the FP32 V-cycle, AMG/config.hpp:4)
+template <int TPR, int RPG, bool UNIT, class VT, class Epi>
+__global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr, const int *__restrict__ col, const VT *__restrict__ val, const VT *__restrict__ x, int row_start, int num_rows, int skip_len, Epi epi)
 {
     constexpr int RPW = 32 / TPR; // rows per warp and pass
     const int lane = threadIdx.x % TPR;
@@ -34,7 +35,7 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
     {
         int j[RPG], e[RPG];
         bool skip[RPG];
-        double acc[RPG];
+        VT acc[RPG];
 #pragma unroll
         for (int g = 0; g < RPG; g++)
         {
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
             skip[g] = e[g] - s > skip_len; // a listed long row: k_spmv_long owns it
             if (skip[g]) e[g] = s;
             j[g] = s + lane;
-            acc[g] = 0.0;
+            acc[g] = VT(0);
         }
         if constexpr (RPG == 1)
         {
@@ -57,13 +58,13 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
             while (more)
             {
                 int c[RPG];
-                double v[RPG];
+                VT v[RPG];
 #pragma unroll
                 for (int g = 0; g < RPG; g++)
                 {
                     const bool on = j[g] < e[g];
                     c[g] = on ? col[j[g]] : 0;
-                    v[g] = (on && !UNIT) ? val[j[g]] : 1.0;
+                    v[g] = (on && !UNIT) ? val[j[g]] : VT(1);
                 }
                 more = false;
 #pragma unroll
@@ -91,15 +92,15 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
 // matrix, and the columns of its Q that become rows of Q^T) outlasts the rest of the kernel.  A matrix descriptor can carry the
 // list of its rows longer than a threshold (prfdd_csr_matrix::long_rows): the row-group kernels then skip those rows and
 // k_spmv_long gives each a whole warp.  Same epilogue, fixed summation order.
-template <bool UNIT, class Epi>
-__global__ void __launch_bounds__(kSpThreads) k_spmv_long(const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, const int *__restrict__ rows, int count, int num_rows, Epi epi)
+template <bool UNIT, class VT, class Epi>
+__global__ void __launch_bounds__(kSpThreads) k_spmv_long(const int *__restrict__ ptr, const int *__restrict__ col, const VT *__restrict__ val, const VT *__restrict__ x, const int *__restrict__ rows, int count, int num_rows, Epi epi)
 {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (kSpThreads / 32) + (threadIdx.x >> 5);
     if (w >= count) return; // whole warps leave together
     const int row = rows[w];
     if (row >= num_rows) return;
-    double acc = 0.0;
+    VT acc = VT(0);
     for (int j = ptr[row] + lane; j < ptr[row + 1]; j += 32) acc += UNIT ? x[col[j]] : val[j] * x[col[j]];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -107,47 +108,59 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv_long(const int *__restrict_
 }
 
 // one entry per row (ptr == NULL): out = epi(row, [val] x[col[row]])  -- Q of a conforming region
-template <bool UNIT, class Epi>
-__global__ void __launch_bounds__(256) k_spmv_single(const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, int row_start, int num_rows, Epi epi)
+template <bool UNIT, class VT, class Epi>
+__global__ void __launch_bounds__(256) k_spmv_single(const int *__restrict__ col, const VT *__restrict__ val, const VT *__restrict__ x, int row_start, int num_rows, Epi epi)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long r = row_start + (long long)blockIdx.x * blockDim.x + threadIdx.x; r < row_start + num_rows; r += stride) epi((int)r, UNIT ? x[col[r]] : val[r] * x[col[r]]);
 }
 
-template <int TPR, bool UNIT, class Epi>
-static void launch_spmv(const prfdd_csr_matrix &A, const double *x, int row_start, int num_rows, bool lr, cudaStream_t st, Epi epi)
+// the descriptor as the kernels see it, for either value type
+template <class VT>
+struct CsrView
+{
+    const int *ptr, *col;
+    const VT *val;
+    int num_rows, num_cols, num_nnz, threads_per_row;
+    const int *long_rows;
+    int num_long_rows, long_row_threshold;
+};
+static CsrView<double> view(const prfdd_csr_matrix &A) { return {A.ptr, A.col, A.val, A.num_rows, A.num_cols, A.num_nnz, A.threads_per_row, A.long_rows, A.num_long_rows, A.long_row_threshold}; }
+static CsrView<float> view(const prfdd_csr_matrix_f32 &A) { return {A.ptr, A.col, A.val, A.num_rows, A.num_cols, A.num_nnz, A.threads_per_row, A.long_rows, A.num_long_rows, A.long_row_threshold}; }
+
+template <int TPR, bool UNIT, class VT, class Epi>
+static void launch_spmv(const CsrView<VT> &A, const VT *x, int row_start, int num_rows, bool lr, cudaStream_t st, Epi epi)
 {
     // two rows per sub-warp once the matrix is large enough to fill the machine with half as many warps
     // (AMG level 1 of the 16^3 N=7 problem, 27 entries/row: 54.9 -> 49.1 us; profiles/r1_notes.txt)
     const bool two = TPR >= 4 && (long long)num_rows * TPR >= (1ll << 21);
     const int grid = stream_grid((long long)num_rows * TPR / (two ? 2 : 1), kSpThreads, 1, 16);
     const int skip_len = lr ? A.long_row_threshold : 0x7fffffff;
-    if (two) k_spmv<TPR, 2, UNIT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
-    else k_spmv<TPR, 1, UNIT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
-    if (lr) k_spmv_long<UNIT><<<(A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
+    if (two) k_spmv<TPR, 2, UNIT, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
+    else k_spmv<TPR, 1, UNIT, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
+    if (lr) k_spmv_long<UNIT, VT><<<(A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
 }
 
-// dispatch on the descriptor
-// epi_bytes: algorithmic bytes per row of the epilogue's operands
-template <class Epi>
-static int spmv(const prfdd_csr_matrix &A, const double *x, int row_start, int num_rows, cudaStream_t st, double epi_bytes, Epi epi)
+// dispatch on the descriptor.  epi_bytes: algorithmic bytes per row of the epilogue's operands
+template <class VT, class Epi>
+static int spmv(const CsrView<VT> &A, const VT *x, int row_start, int num_rows, cudaStream_t st, double epi_bytes, Epi epi)
 {
     if (num_rows <= 0) return 0;
     if (!A.col) return -8;
     const bool unit = A.val == nullptr;
-    // algorithmic bytes: col 4 (+ val 8) per entry, ptr 4 per row, the gathered vector once, the epilogue's operands
+    // algorithmic bytes: col 4 (+ val) per entry, ptr 4 per row, the gathered vector once, the epilogue's operands
     double bytes = epi_bytes * num_rows;
     if (x)
     {
         const double entries = !A.ptr ? (double)num_rows : (num_rows == A.num_rows && A.num_nnz >= 0) ? (double)A.num_nnz : 0.0;
-        bytes += (unit ? 4.0 : 12.0) * entries + (A.ptr ? 4.0 * (num_rows + 1) : 0.0) + 8.0 * (A.num_cols > 0 ? A.num_cols : num_rows);
+        bytes += (unit ? 4.0 : 4.0 + sizeof(VT)) * entries + (A.ptr ? 4.0 * (num_rows + 1) : 0.0) + (double)sizeof(VT) * (A.num_cols > 0 ? A.num_cols : num_rows);
     }
     if (!A.ptr)
     {
         // one entry per row
         if (!x) return -8;
-        if (unit) k_spmv_single<true><<<stream_grid(num_rows, 256, 2, 8), 256, 0, st>>>(A.col, nullptr, x, row_start, num_rows, epi);
-        else k_spmv_single<false><<<stream_grid(num_rows, 256, 2, 8), 256, 0, st>>>(A.col, A.val, x, row_start, num_rows, epi);
+        if (unit) k_spmv_single<true, VT><<<stream_grid(num_rows, 256, 2, 8), 256, 0, st>>>(A.col, nullptr, x, row_start, num_rows, epi);
+        else k_spmv_single<false, VT><<<stream_grid(num_rows, 256, 2, 8), 256, 0, st>>>(A.col, A.val, x, row_start, num_rows, epi);
         return launched(bytes);
     }
     const int tpr = A.threads_per_row > 0 ? A.threads_per_row : 4;
@@ -157,10 +170,10 @@ static int spmv(const prfdd_csr_matrix &A, const double *x, int row_start, int n
         // matrices without values are Q^T-like: short rows
         switch (tpr)
         {
-        case 1: launch_spmv<1, true>(A, x, row_start, num_rows, lr, st, epi); break;
-        case 2: launch_spmv<2, true>(A, x, row_start, num_rows, lr, st, epi); break;
-        case 4: launch_spmv<4, true>(A, x, row_start, num_rows, lr, st, epi); break;
-        case 8: launch_spmv<8, true>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 1: launch_spmv<1, true, VT>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 2: launch_spmv<2, true, VT>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 4: launch_spmv<4, true, VT>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 8: launch_spmv<8, true, VT>(A, x, row_start, num_rows, lr, st, epi); break;
         default: return -6;
         }
     }
@@ -168,17 +181,114 @@ static int spmv(const prfdd_csr_matrix &A, const double *x, int row_start, int n
     {
         switch (tpr)
         {
-        case 1: launch_spmv<1, false>(A, x, row_start, num_rows, lr, st, epi); break;
-        case 2: launch_spmv<2, false>(A, x, row_start, num_rows, lr, st, epi); break;
-        case 4: launch_spmv<4, false>(A, x, row_start, num_rows, lr, st, epi); break;
-        case 8: launch_spmv<8, false>(A, x, row_start, num_rows, lr, st, epi); break;
-        case 16: launch_spmv<16, false>(A, x, row_start, num_rows, lr, st, epi); break;
-        case 32: launch_spmv<32, false>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 1: launch_spmv<1, false, VT>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 2: launch_spmv<2, false, VT>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 4: launch_spmv<4, false, VT>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 8: launch_spmv<8, false, VT>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 16: launch_spmv<16, false, VT>(A, x, row_start, num_rows, lr, st, epi); break;
+        case 32: launch_spmv<32, false, VT>(A, x, row_start, num_rows, lr, st, epi); break;
         default: return -6;
         }
     }
     if (lr) prfdd_launch_count_add(1);
     return launched(bytes);
+}
+
+// ---- the SpMV family, once for both value types -----------------------------------------------------------------------
+template <class VT>
+static int t_multiply(VT *Au, const CsrView<VT> &A, const VT *u, cudaStream_t st)
+{
+    return spmv(A, u, 0, A.num_rows, st, 1.0 * sizeof(VT), [=] __device__(int row, VT ax) { Au[row] = ax; });
+}
+template <class VT>
+static int t_multiply_range(VT *Au, const CsrView<VT> &A, const VT *u, int row_start, int row_end, cudaStream_t st)
+{
+    if (row_end < row_start) return -7; // csr_matrix.tpp:319-323
+    return spmv(A, u, row_start, row_end - row_start + 1, st, 1.0 * sizeof(VT), [=] __device__(int row, VT ax) { Au[row] = ax; });
+}
+template <class VT>
+static int t_multiply_weight(VT *Au, const CsrView<VT> &A, const VT *u, const VT *weight, cudaStream_t st)
+{
+    return spmv(A, u, 0, A.num_rows, st, 2.0 * sizeof(VT), [=] __device__(int row, VT ax) { Au[row] = ax * weight[row]; });
+}
+template <class VT>
+static int t_matvec(VT *y, const CsrView<VT> &A, const VT *x, VT alpha, VT beta, cudaStream_t st)
+{
+    if (beta == VT(0))
+        return spmv(A, x, 0, A.num_rows, st, 1.0 * sizeof(VT), [=] __device__(int row, VT ax) { y[row] = alpha * ax; });
+    return spmv(A, x, 0, A.num_rows, st, 2.0 * sizeof(VT), [=] __device__(int row, VT ax) { y[row] = alpha * ax + beta * y[row]; });
+}
+template <class VT>
+static int t_residual(VT *v, const CsrView<VT> &A, const VT *u, const VT *f, cudaStream_t st)
+{
+    return spmv(A, u, 0, A.num_rows, st, 2.0 * sizeof(VT), [=] __device__(int row, VT ax) { v[row] = f[row] - ax; });
+}
+template <class VT>
+static int t_cheby_residual(VT *r, VT *t, const CsrView<VT> &A, const VT *u, const VT *f, const VT *ds, VT c_hi, cudaStream_t st)
+{
+    // u == NULL: u = 0, the product A u is skipped (x == nullptr in k_spmv) and the launch shape is irrelevant
+    CsrView<VT> B = A;
+    if (!u) B.threads_per_row = 1;
+    return spmv(B, u, 0, A.num_rows, st, 4.0 * sizeof(VT), [=] __device__(int row, VT ax) {
+        const VT d = ds[row];
+        const VT rr = d * (f[row] - ax);
+        r[row] = rr;
+        t[row] = d * (c_hi * rr);
+    });
+}
+template <class VT>
+static int t_restrict_cheby_residual(VT *f, VT *r, VT *t, const CsrView<VT> &R, const VT *v, const VT *ds, VT c_hi, cudaStream_t st)
+{
+    // f = R v fused with the zero-guess head of the coarse level's smoothing: r = ds f, t = ds (c_hi r)
+    return spmv(R, v, 0, R.num_rows, st, 4.0 * sizeof(VT), [=] __device__(int row, VT ax) {
+        const VT d = ds[row];
+        const VT rr = d * ax;
+        f[row] = ax;
+        r[row] = rr;
+        t[row] = d * (c_hi * rr);
+    });
+}
+template <class VT>
+static int t_cheby_step(VT *u, VT *t_out, const CsrView<VT> &A, const VT *t_in, const VT *r, const VT *ds, VT c, int last, int u_is_zero, cudaStream_t st)
+{
+    if (last)
+    {
+        if (u_is_zero)
+            return spmv(A, t_in, 0, A.num_rows, st, 3.0 * sizeof(VT), [=] __device__(int row, VT ax) {
+                const VT d = ds[row];
+                u[row] = d * (c * r[row] + d * ax);
+            });
+        return spmv(A, t_in, 0, A.num_rows, st, 4.0 * sizeof(VT), [=] __device__(int row, VT ax) {
+            const VT d = ds[row];
+            u[row] += d * (c * r[row] + d * ax);
+        });
+    }
+    return spmv(A, t_in, 0, A.num_rows, st, 3.0 * sizeof(VT), [=] __device__(int row, VT ax) {
+        const VT d = ds[row];
+        t_out[row] = d * (c * r[row] + d * ax);
+    });
+}
+
+// dense x = M b for both value types (k_dense_solve above is the double instance)
+template <class VT>
+__global__ void __launch_bounds__(256) k_dense_t(VT *__restrict__ x, const VT *__restrict__ M, const VT *__restrict__ b, int n)
+{
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n) return; // whole warps leave together
+    const VT *__restrict__ row = M + (size_t)r * n;
+    VT acc = VT(0);
+    for (int c = lane; c < n; c += 32) acc += row[c] * b[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) x[r] = acc;
+}
+
+template <class A, class B>
+__global__ void __launch_bounds__(256) k_cast(A *__restrict__ dst, const B *__restrict__ src, long long n)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (A)src[i];
 }
 
 // the pointer-argument entry points (the reference's kernel signatures + one lanes-per-row hint): no long-row list, no staging
@@ -334,77 +444,55 @@ int prfdd_csr_plan(prfdd_csr_matrix *A, const int *ptr_host, int *long_rows_host
 }
 
 // ---- descriptor entry points ----------------------------------------------------------------
-int prfdd_csrm_multiply(double *Au, const prfdd_csr_matrix *A, const double *u, prfdd_stream_t stream)
+int prfdd_csrm_multiply(double *Au, const prfdd_csr_matrix *A, const double *u, prfdd_stream_t stream) { return t_multiply(Au, view(*A), u, S(stream)); }
+int prfdd_csrm_multiply_range(double *Au, const prfdd_csr_matrix *A, const double *u, int row_start, int row_end, prfdd_stream_t stream) { return t_multiply_range(Au, view(*A), u, row_start, row_end, S(stream)); }
+int prfdd_csrm_multiply_weight(double *Au, const prfdd_csr_matrix *A, const double *u, const double *weight, prfdd_stream_t stream) { return t_multiply_weight(Au, view(*A), u, weight, S(stream)); }
+int prfdd_csrm_matvec(double *y, const prfdd_csr_matrix *A, const double *x, double alpha, double beta, prfdd_stream_t stream) { return t_matvec(y, view(*A), x, alpha, beta, S(stream)); }
+int prfdd_csrm_residual(double *v, const prfdd_csr_matrix *A, const double *u, const double *f, prfdd_stream_t stream) { return t_residual(v, view(*A), u, f, S(stream)); }
+int prfdd_csrm_cheby_residual(double *r, double *t, const prfdd_csr_matrix *A, const double *u, const double *f, const double *ds, double c_hi, prfdd_stream_t stream) { return t_cheby_residual(r, t, view(*A), u, f, ds, c_hi, S(stream)); }
+int prfdd_csrm_restrict_cheby_residual(double *f, double *r, double *t, const prfdd_csr_matrix *R, const double *v, const double *ds, double c_hi, prfdd_stream_t stream) { return t_restrict_cheby_residual(f, r, t, view(*R), v, ds, c_hi, S(stream)); }
+int prfdd_csrm_cheby_step(double *u, double *t_out, const prfdd_csr_matrix *A, const double *t_in, const double *r, const double *ds, double c, int last, int u_is_zero, prfdd_stream_t stream) { return t_cheby_step(u, t_out, view(*A), t_in, r, ds, c, last, u_is_zero, S(stream)); }
+
+// FP32 instances: the V-cycle with `Float float` (AMG/config.hpp:4)
+int prfdd_csrm_multiply_f32(float *Au, const prfdd_csr_matrix_f32 *A, const float *u, prfdd_stream_t stream) { return t_multiply(Au, view(*A), u, S(stream)); }
+int prfdd_csrm_matvec_f32(float *y, const prfdd_csr_matrix_f32 *A, const float *x, float alpha, float beta, prfdd_stream_t stream) { return t_matvec(y, view(*A), x, alpha, beta, S(stream)); }
+int prfdd_csrm_residual_f32(float *v, const prfdd_csr_matrix_f32 *A, const float *u, const float *f, prfdd_stream_t stream) { return t_residual(v, view(*A), u, f, S(stream)); }
+int prfdd_csrm_cheby_residual_f32(float *r, float *t, const prfdd_csr_matrix_f32 *A, const float *u, const float *f, const float *ds, float c_hi, prfdd_stream_t stream) { return t_cheby_residual(r, t, view(*A), u, f, ds, c_hi, S(stream)); }
+int prfdd_csrm_restrict_cheby_residual_f32(float *f, float *r, float *t, const prfdd_csr_matrix_f32 *R, const float *v, const float *ds, float c_hi, prfdd_stream_t stream) { return t_restrict_cheby_residual(f, r, t, view(*R), v, ds, c_hi, S(stream)); }
+int prfdd_csrm_cheby_step_f32(float *u, float *t_out, const prfdd_csr_matrix_f32 *A, const float *t_in, const float *r, const float *ds, float c, int last, int u_is_zero, prfdd_stream_t stream) { return t_cheby_step(u, t_out, view(*A), t_in, r, ds, c, last, u_is_zero, S(stream)); }
+
+int prfdd_dense_solve_f32(float *x, const float *Ainv, const float *b, int n, prfdd_stream_t stream)
 {
-    return spmv(*A, u, 0, A->num_rows, S(stream), 8.0, [=] __device__(int row, double ax) { Au[row] = ax; });
+    if (n <= 0) return 0;
+    k_dense_t<float><<<(n + 7) / 8, 256, 0, S(stream)>>>(x, Ainv, b, n);
+    return launched(4.0 * n * (double)n + 8.0 * n);
 }
 
-int prfdd_csrm_multiply_range(double *Au, const prfdd_csr_matrix *A, const double *u, int row_start, int row_end, prfdd_stream_t stream)
+int prfdd_cast_f64_to_f32(float *dst, const double *src, int n, prfdd_stream_t stream)
 {
-    if (row_end < row_start) return -7; // csr_matrix.tpp:319-323
-    return spmv(*A, u, row_start, row_end - row_start + 1, S(stream), 8.0, [=] __device__(int row, double ax) { Au[row] = ax; });
+    if (n <= 0) return 0;
+    k_cast<float, double><<<stream_grid(n, 256, 2, 8), 256, 0, S(stream)>>>(dst, src, n);
+    return launched(12.0 * n);
 }
 
-int prfdd_csrm_multiply_weight(double *Au, const prfdd_csr_matrix *A, const double *u, const double *weight, prfdd_stream_t stream)
+int prfdd_cast_f32_to_f64(double *dst, const float *src, int n, prfdd_stream_t stream)
 {
-    return spmv(*A, u, 0, A->num_rows, S(stream), 16.0, [=] __device__(int row, double ax) { Au[row] = ax * weight[row]; });
+    if (n <= 0) return 0;
+    k_cast<double, float><<<stream_grid(n, 256, 2, 8), 256, 0, S(stream)>>>(dst, src, n);
+    return launched(12.0 * n);
 }
 
-int prfdd_csrm_matvec(double *y, const prfdd_csr_matrix *A, const double *x, double alpha, double beta, prfdd_stream_t stream)
+int prfdd_cheby_order1_f32(float *u, const float *r, const float *ds, float c, int u_is_zero, int size, prfdd_stream_t stream)
 {
-    if (beta == 0.0)
-        return spmv(*A, x, 0, A->num_rows, S(stream), 8.0, [=] __device__(int row, double ax) { y[row] = alpha * ax; });
-    return spmv(*A, x, 0, A->num_rows, S(stream), 16.0, [=] __device__(int row, double ax) { y[row] = alpha * ax + beta * y[row]; });
-}
-
-int prfdd_csrm_residual(double *v, const prfdd_csr_matrix *A, const double *u, const double *f, prfdd_stream_t stream)
-{
-    return spmv(*A, u, 0, A->num_rows, S(stream), 16.0, [=] __device__(int row, double ax) { v[row] = f[row] - ax; });
-}
-
-int prfdd_csrm_cheby_residual(double *r, double *t, const prfdd_csr_matrix *A, const double *u, const double *f, const double *ds, double c_hi, prfdd_stream_t stream)
-{
-    // u == NULL: u = 0, the product A u is skipped (x == nullptr in k_spmv) and the launch shape is irrelevant
-    prfdd_csr_matrix B = *A;
-    if (!u) B.threads_per_row = 1;
-    return spmv(B, u, 0, A->num_rows, S(stream), 32.0, [=] __device__(int row, double ax) {
-        const double d = ds[row];
-        const double rr = d * (f[row] - ax);
-        r[row] = rr;
-        t[row] = d * (c_hi * rr);
-    });
-}
-
-int prfdd_csrm_restrict_cheby_residual(double *f, double *r, double *t, const prfdd_csr_matrix *R, const double *v, const double *ds, double c_hi, prfdd_stream_t stream)
-{
-    // f = R v fused with the zero-guess head of the coarse level's smoothing: r = ds f, t = ds (c_hi r)
-    return spmv(*R, v, 0, R->num_rows, S(stream), 32.0, [=] __device__(int row, double ax) {
-        const double d = ds[row];
-        const double rr = d * ax;
-        f[row] = ax;
-        r[row] = rr;
-        t[row] = d * (c_hi * rr);
-    });
-}
-
-int prfdd_csrm_cheby_step(double *u, double *t_out, const prfdd_csr_matrix *A, const double *t_in, const double *r, const double *ds, double c, int last, int u_is_zero, prfdd_stream_t stream)
-{
-    if (last)
-    {
-        if (u_is_zero)
-            return spmv(*A, t_in, 0, A->num_rows, S(stream), 24.0, [=] __device__(int row, double ax) {
-                const double d = ds[row];
-                u[row] = d * (c * r[row] + d * ax);
-            });
-        return spmv(*A, t_in, 0, A->num_rows, S(stream), 32.0, [=] __device__(int row, double ax) {
-            const double d = ds[row];
-            u[row] += d * (c * r[row] + d * ax);
-        });
-    }
-    return spmv(*A, t_in, 0, A->num_rows, S(stream), 24.0, [=] __device__(int row, double ax) {
-        const double d = ds[row];
-        t_out[row] = d * (c * r[row] + d * ax);
-    });
+    // first-order smoother tail in FP32 (the FP64 form lives in k_vector.cu): one launch of the element-wise epilogue, no product
+    prfdd_csr_matrix_f32 none = {};
+    int dummy = 0;
+    none.col = &dummy; none.num_rows = size; none.threads_per_row = 1;
+    static const int zero_ptr = 0;
+    none.ptr = &zero_ptr; // never read: x == NULL skips the row walk
+    if (u_is_zero)
+        return spmv(view(none), (const float *)nullptr, 0, size, S(stream), 12.0, [=] __device__(int row, float) { u[row] = ds[row] * (c * r[row]); });
+    return spmv(view(none), (const float *)nullptr, 0, size, S(stream), 16.0, [=] __device__(int row, float) { u[row] += ds[row] * (c * r[row]); });
 }
 
 // ---- pointer entry points: the reference's kernel arguments + one lanes-per-row hint ------------

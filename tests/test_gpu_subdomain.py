@@ -115,3 +115,41 @@ def test_solve_matches_golden_history(prfdd, tmp_path, case):
     assert nit == case["iterations"] and len(hist) == len(ref)
     assert np.abs(hist - ref).max() <= 1e-9 * ref[0]
     S.close()
+
+
+@pytest.mark.parametrize("dim,nel,N,r,eps", [(3, 4, 7, 3, 0.0), (3, 3, 4, 3, 0.05), (2, 16, 7, 3, 0.0)])
+def test_fp32_vcycle_parity(prfdd, tmp_path, dim, nel, N, r, eps):
+    """SURVEY 8f N3, the AMG half: `Float float` (AMG/config.hpp:4) -- FP32 hierarchy, smoother and cycle under the FP64 Krylov
+    methods.  The oracle restates it with its own FP32 loops (liboracle_f32.so); FP32 sums are order dependent, so the bar is the
+    FP32 one: one V-cycle to 2e-5 of its norm, the SAME outer iteration count as the FP32 oracle and as the FP64 solve, residual
+    history to 1e-4, and the converged solution as close to the manufactured one as the FP64 solve's."""
+    _need_gpu()
+    d = str(tmp_path)
+    prfdd.mesh_generate_box(d, dim, nel, N, 1, eps, reduction=r)
+    W = odomain.DomainWorld(d, N, 1)
+    Sd32 = osub.SubdomainWorld(W, d, N, r, amg_precision="float")
+    So = Sd32.ranks[0]
+    S = prfdd.Solver(d, poly_degree=N, poly_reduction=r, amg_precision=1)
+    assert np.array_equal(S.get_array("AMG_LEVEL_ROWS"), [L.n for L in So.amg.levels])
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal(So.num_dofs)
+    ref = So.amg.vcycle(b, 1).astype(np.float64)
+    got = S.apply("VCYCLE", b)
+    assert np.linalg.norm(got - ref) <= 2e-5 * np.linalg.norm(ref)
+    S.setup_problem(4)
+    us = W.initial_function(4)
+    f = W.new_vector(); W.stiffness_matrix(f, us)
+    u = W.new_vector(); W.flexible_conjugate_gradient(u, f, Sd32)
+    h32 = np.array(W.history)
+    nit, hist = S.solve(0)
+    assert nit == W.num_iterations and len(hist) == len(h32)
+    assert np.max(np.abs(hist - h32) / h32) <= 1e-4
+    ug = S.get_array("U")
+    S64 = prfdd.Solver(d, poly_degree=N, poly_reduction=r)
+    S64.setup_problem(4)
+    n64, h64 = S64.solve(0)
+    assert n64 == nit                                     # the flexible outer method does not notice the FP32 preconditioner
+    e32 = np.linalg.norm(ug - us[0]) / np.linalg.norm(us[0])
+    e64 = np.linalg.norm(S64.get_array("U") - us[0]) / np.linalg.norm(us[0])
+    assert e32 <= 2.0 * e64 + 1e-9
+    S.close(); S64.close()
