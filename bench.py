@@ -387,8 +387,8 @@ def main():
         mesh_dir = tempfile.mkdtemp(prefix="prfdd_bench_")
     use_pc = 0 if os.environ.get("PRFDD_BENCH_NO_PC") else 1
     t_setup0 = time.perf_counter()
-    if rank == 0:
-        pr.mesh_generate_box(mesh_dir, 3, tuple(nel), N_DEG, world, args.eps, reduction=REDUCTION if use_pc else None)
+    # every rank writes its own part of the mesh
+    pr.mesh_generate_box(mesh_dir, 3, tuple(nel), N_DEG, world, args.eps, reduction=REDUCTION if use_pc else None, only_rank=rank if world > 1 else -1)
     if world > 1:
         dist.barrier()
     mesh_s = time.perf_counter() - t_setup0

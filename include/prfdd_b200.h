@@ -399,6 +399,9 @@ void prfdd_glibc_rand_fill(double *out, long long n, unsigned int seed);
  * block-partitioned over num_procs ranks (power of two); eps = smooth deformation amplitude */
 int prfdd_mesh_generate_box(const char *directory, int dim, const int nel[3], int poly_degree, int num_procs,
                             double eps);
+/* the same, writing only the files of rank `only_rank` (every rank of a multi-GPU job writes its own part; -1 = all) */
+int prfdd_mesh_generate_box_rank(const char *directory, int dim, const int nel[3], int poly_degree, int num_procs,
+                                 double eps, int only_rank);
 
 /* ---------------------------------------------------------------------------------------------
  * halo lists for the process-boundary sum (host logic of Domain::setup_halo; stands where gslib_gs_setup stands,

@@ -65,14 +65,14 @@ def ladder(N, r):
     return out
 
 
-def mesh_generate_box(directory, dim, nel, N, num_procs=1, eps=0.0, reduction=None):
-    """Writes the mesh for degree N (and, if reduction is given, for every degree of the ladder)."""
+def mesh_generate_box(directory, dim, nel, N, num_procs=1, eps=0.0, reduction=None, only_rank=-1):
+    """Writes the mesh for degree N (and, if reduction is given, for every degree of the ladder); only_rank >= 0: that rank's files only."""
     if isinstance(nel, int):
         nel = (nel,) * dim
     nel3 = (C.c_int * 3)(*(list(nel) + [1] * (3 - len(nel))))
     degrees = ladder(N, reduction) if reduction else [N]
     for n in degrees:
-        check(lib().prfdd_mesh_generate_box(directory.encode(), C.c_int(dim), nel3, C.c_int(n), C.c_int(num_procs), C.c_double(eps)), "mesh_generate_box")
+        check(lib().prfdd_mesh_generate_box_rank(directory.encode(), C.c_int(dim), nel3, C.c_int(n), C.c_int(num_procs), C.c_double(eps), C.c_int(only_rank)), "mesh_generate_box")
 
 
 class Solver:

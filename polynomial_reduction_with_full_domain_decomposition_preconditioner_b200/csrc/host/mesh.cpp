@@ -47,7 +47,14 @@ void dump(const std::string &dir, const char *name, int p, int N, const std::vec
 }
 } // namespace
 
+extern "C" int prfdd_mesh_generate_box_rank(const char *directory, int dimn, const int nel_in[3], int N, int nranks, double eps, int only_rank);
+
 extern "C" int prfdd_mesh_generate_box(const char *directory, int dimn, const int nel_in[3], int N, int nranks, double eps)
+{
+    return prfdd_mesh_generate_box_rank(directory, dimn, nel_in, N, nranks, eps, -1);
+}
+
+extern "C" int prfdd_mesh_generate_box_rank(const char *directory, int dimn, const int nel_in[3], int N, int nranks, double eps, int only_rank)
 {
     try
     {
@@ -115,6 +122,7 @@ extern "C" int prfdd_mesh_generate_box(const char *directory, int dimn, const in
 
         for (int p = 0; p < nranks; p++)
         {
+            if (only_rank >= 0 && p != only_rank) continue;
             const int pc[3] = {p % L.P[0], (p / L.P[0]) % L.P[1], p / (L.P[0] * L.P[1])};
             const long long E = (long long)bl[0] * bl[1] * bl[2];
             std::vector<double> x(E * npts), y(E * npts), zc(E * npts), mask(E * npts);
