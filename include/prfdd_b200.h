@@ -145,12 +145,34 @@ typedef struct prfdd_csr_matrix
     const int *long_rows;
     int num_long_rows;
     int long_row_threshold;
+    /* optional sliced copy of the same matrix (prfdd_sell_layout / prfdd_sell_fill): when sell_col is set, full products
+     * (all rows, x given) read it instead of ptr/col/val; the arithmetic and its order are those of the row kernels */
+    const int *sell_off;    /* [sell_num_slices + 1] first entry of each slice, multiples of 32 */
+    const int *sell_col;    /* [sell_off[sell_num_slices]] */
+    const double *sell_val;
+    const int *sell_row;    /* [sell_num_slices * 32 / sell_lanes] row of each slot, -1: none; NULL: slot = row */
+    int sell_num_slices;
+    int sell_lanes;         /* lanes per row: 1, 2, 4, 8, 16 or 32 */
+    int sell_window;        /* window_rows the layout was sorted with (0: row order); 256 selects the CTA-per-window kernel */
 } prfdd_csr_matrix;
 /* host-side planning: sets threads_per_row and long_row_threshold of *A from
  * ptr_host[0..num_rows] (A->num_rows must be set; A->num_nnz is set to ptr_host[num_rows]).  The rows longer than the
  * threshold are written to long_rows_host (capacity entries) and their count is returned (0: no list needed; the caller
  * uploads the list and sets A->long_rows / A->num_long_rows).  Returns -(count) if the capacity is too small. */
 int prfdd_csr_plan(prfdd_csr_matrix *A, const int *ptr_host, int *long_rows_host, int capacity);
+/* Sliced layout (SELL-C-sigma with `lanes` lanes per row): 32/lanes consecutive slots form a slice; entry k*lanes + t of the
+ * row in slot q of a slice sits at sell_off[slice] + 32*k + q*lanes + t, so one warp load of col (or val) is one contiguous
+ * 128 (256) byte line whatever the row lengths -- the row kernels' strided segments cost an L1 tag look-up per segment,
+ * which is what bounds them (profiles/r2_notes.txt).  Slices are padded to their longest row (value 0); rows are sorted by
+ * length inside windows of window_rows consecutive rows (0: keep the order) to keep the padding small.
+ * prfdd_sell_layout: fills slice_off_host[num_slices + 1] and slot_row_host[num_slices * 32 / lanes] (-1: empty slot),
+ * num_slices = ceil(num_rows / (32/lanes)); returns the padded entry count, or < 0.
+ * prfdd_sell_fill_*: writes the padded col/val arrays of that layout. */
+long long prfdd_sell_layout(const int *ptr_host, int num_rows, int lanes, int window_rows, int *slice_off_host, int *slot_row_host);
+int prfdd_sell_fill(const int *ptr_host, const int *col_host, const double *val_host, int num_rows, int lanes,
+                    const int *slice_off_host, const int *slot_row_host, int *sell_col_host, double *sell_val_host);
+int prfdd_sell_fill_f32(const int *ptr_host, const int *col_host, const double *val_host, int num_rows, int lanes,
+                        const int *slice_off_host, const int *slot_row_host, int *sell_col_host, float *sell_val_host);
 /* descriptor forms of the entry points below (same arithmetic, same epilogues) */
 int prfdd_csrm_multiply(double *Au, const prfdd_csr_matrix *A, const double *u, prfdd_stream_t stream);
 int prfdd_csrm_multiply_range(double *Au, const prfdd_csr_matrix *A, const double *u, int row_start, int row_end, prfdd_stream_t stream);
@@ -229,6 +251,13 @@ typedef struct prfdd_csr_matrix_f32
     const int *long_rows;
     int num_long_rows;
     int long_row_threshold;
+    const int *sell_off;
+    const int *sell_col;
+    const float *sell_val;
+    const int *sell_row;
+    int sell_num_slices;
+    int sell_lanes;
+    int sell_window;
 } prfdd_csr_matrix_f32;
 int prfdd_csrm_multiply_f32(float *Au, const prfdd_csr_matrix_f32 *A, const float *u, prfdd_stream_t stream);
 int prfdd_csrm_matvec_f32(float *y, const prfdd_csr_matrix_f32 *A, const float *x, float alpha, float beta, prfdd_stream_t stream);

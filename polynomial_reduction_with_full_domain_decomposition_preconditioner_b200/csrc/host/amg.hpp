@@ -686,6 +686,7 @@ struct DeviceCSR
 {
     int num_rows = 0, num_cols = 0, nnz = 0, tpr = 4;
     dev::memory ptr, col, val, long_rows;
+    dev::memory sell_off, sell_col, sell_val, sell_row; // sliced copy (prfdd_sell_layout) read by the full products
     prfdd_csr_matrix desc = {};       // device arrays + launch plan, as the C ABI takes them (FP64 values)
     prfdd_csr_matrix_f32 desc32 = {}; // the same with FP32 values (fp32 upload)
     void upload(const HostCSR &A, bool fp32 = false)
@@ -719,7 +720,68 @@ struct DeviceCSR
         desc32.ptr = desc.ptr; desc32.col = desc.col; desc32.val = fp32 ? val.as<float>() : nullptr;
         desc32.num_rows = num_rows; desc32.num_cols = num_cols; desc32.num_nnz = desc.num_nnz; desc32.threads_per_row = desc.threads_per_row;
         desc32.long_rows = desc.long_rows; desc32.num_long_rows = desc.num_long_rows; desc32.long_row_threshold = desc.long_row_threshold;
+        build_sell(A, fp32);
         if (fp32) { desc.val = nullptr; desc.col = nullptr; } // no FP64 values exist: an FP64 call on this matrix fails loudly (-8)
+    }
+    // the sliced copy for matrices large enough to be bound by the memory system rather than by the launch
+    void build_sell(const HostCSR &A, bool fp32)
+    {
+        static const int enabled = getenv("PRFDD_SELL") ? atoi(getenv("PRFDD_SELL")) : 1;
+        static const int min_rows = getenv("PRFDD_SELL_MIN_ROWS") ? atoi(getenv("PRFDD_SELL_MIN_ROWS")) : 8192;
+        static const int window = getenv("PRFDD_SELL_WINDOW") ? atoi(getenv("PRFDD_SELL_WINDOW")) : 256;
+        static const int force_lanes = getenv("PRFDD_SELL_LANES") ? atoi(getenv("PRFDD_SELL_LANES")) : 0;
+        static const bool verbose = getenv("PRFDD_SELL_VERBOSE") != nullptr;
+        if (!enabled || num_rows < min_rows || nnz == 0) return;
+        // lanes per row of the sliced copy, from the wavefront counts of the c2 hierarchy (profiles/r2_notes.txt): short rows one lane,
+        // ~20-entry rows 2, ~60-entry rows 8; small matrices with long rows 16 (they are latency bound: more slices)
+        const double avg = (double)nnz / num_rows;
+        int lanes = avg <= 10.0 ? 1 : avg <= 32.0 ? 2 : avg <= 48.0 ? 4 : 8;
+        while (lanes < 32 && lanes < avg / 4 && (long long)num_rows * lanes / 32 < 148 * 32) lanes *= 2; // a slice per warp: enough of them to fill the chip
+        if (force_lanes > 0) lanes = force_lanes;
+        const int R = 32 / lanes;
+        const int num_slices = (num_rows + R - 1) / R;
+        std::vector<int> off((size_t)num_slices + 1), slot_row((size_t)num_slices * R);
+        // row order when it pads little (no slot -> row list, contiguous epilogue accesses); else rows sorted by length in windows
+        long long total = prfdd_sell_layout(A.ptr.data(), num_rows, lanes, 0, off.data(), slot_row.data());
+        if (total < 0 || (double)total > 1.03 * nnz) total = prfdd_sell_layout(A.ptr.data(), num_rows, lanes, window, off.data(), slot_row.data());
+        if (total < 0) return; // too large for 32-bit offsets: the row kernels stay
+        bool identity = true;
+        for (int q = 0; q < num_rows && identity; q++) identity = slot_row[q] == q;
+        std::vector<int> scol((size_t)std::max(total, 1ll));
+        sell_off = prfdd_host::device.malloc<int>(num_slices + 1);
+        sell_off.copyFrom(off.data(), (num_slices + 1) * sizeof(int));
+        sell_col = prfdd_host::device.malloc<int>(std::max(total, 1ll));
+        if (fp32)
+        {
+            std::vector<float> sval((size_t)std::max(total, 1ll));
+            prfdd_sell_fill_f32(A.ptr.data(), A.col.data(), A.val.data(), num_rows, lanes, off.data(), slot_row.data(), scol.data(), sval.data());
+            sell_val = prfdd_host::device.malloc<float>(std::max(total, 1ll));
+            sell_val.copyFrom(sval.data(), total * sizeof(float));
+            desc32.sell_val = sell_val.as<float>();
+        }
+        else
+        {
+            std::vector<double> sval((size_t)std::max(total, 1ll));
+            prfdd_sell_fill(A.ptr.data(), A.col.data(), A.val.data(), num_rows, lanes, off.data(), slot_row.data(), scol.data(), sval.data());
+            sell_val = prfdd_host::device.malloc<double>(std::max(total, 1ll));
+            sell_val.copyFrom(sval.data(), total * sizeof(double));
+            desc.sell_val = sell_val.as<double>();
+        }
+        sell_col.copyFrom(scol.data(), total * sizeof(int));
+        if (!identity)
+        {
+            sell_row = prfdd_host::device.malloc<int>(num_slices * R);
+            sell_row.copyFrom(slot_row.data(), (size_t)num_slices * R * sizeof(int));
+        }
+        desc.sell_off = desc32.sell_off = sell_off.as<int>();
+        desc.sell_col = desc32.sell_col = sell_col.as<int>();
+        desc.sell_row = desc32.sell_row = identity ? nullptr : sell_row.as<int>();
+        desc.sell_num_slices = desc32.sell_num_slices = num_slices;
+        desc.sell_lanes = desc32.sell_lanes = lanes;
+        desc.sell_window = desc32.sell_window = identity ? 0 : window;
+        if (verbose)
+            fprintf(stderr, "sell: %d x %d, %d entries (%.1f/row), lanes %d, window %d, %d slices, padded %lld (+%.1f %%), %s order\n", num_rows, num_cols, nnz,
+                    (double)nnz / num_rows, lanes, window, num_slices, total, 100.0 * (total - nnz) / nnz, identity ? "row" : "sorted");
     }
 };
 

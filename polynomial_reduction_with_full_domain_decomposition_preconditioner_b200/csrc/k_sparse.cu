@@ -24,14 +24,31 @@ constexpr int kSpThreads = 256;
 // (rows r, r + 32/TPR, ...), which multiplies the independent col/val -> x load chains a lane has in
 // flight; the long rows of the coarse AMG levels are latency bound without it.
 // VT: value type of the matrix, the gathered vector and the row sums (double; float for the FP32 V-cycle, AMG/config.hpp:4)
-template <int TPR, int RPG, bool UNIT, class VT, class Epi>
+// LOCAL: every CTA walks ONE contiguous slice of the rows (grid = resident CTAs of the whole chip), so the rows an SM works on
+// stay neighbours for the whole launch and the gathers of x entries shared by neighbouring rows hit that SM's L1 instead of
+// being fetched from L2 once per SM that happens to hold one of the rows (the grid-stride form sweeps one chip-wide front).
+template <int TPR, int RPG, bool UNIT, bool LOCAL, class VT, class Epi>
 __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr, const int *__restrict__ col, const VT *__restrict__ val, const VT *__restrict__ x, int row_start, int num_rows, int skip_len, Epi epi)
 {
     constexpr int RPW = 32 / TPR; // rows per warp and pass
     const int lane = threadIdx.x % TPR;
     const int sub = (threadIdx.x & 31) / TPR;
-    const long long rows_per_grid = (long long)gridDim.x * (kSpThreads / TPR) * RPG;
-    for (long long r0 = ((long long)blockIdx.x * (kSpThreads / 32) + (threadIdx.x >> 5)) * RPW * RPG; r0 < num_rows; r0 += rows_per_grid)
+    long long r_begin, r_end, r_step;
+    if constexpr (LOCAL)
+    {
+        constexpr int G = RPW * RPG; // rows of one warp pass: slices start on a multiple of it
+        const long long slice = ((num_rows + (long long)gridDim.x * G - 1) / ((long long)gridDim.x * G)) * G;
+        r_begin = blockIdx.x * slice + (threadIdx.x >> 5) * G;
+        r_end = (blockIdx.x + 1) * slice < num_rows ? (blockIdx.x + 1) * slice : num_rows;
+        r_step = (kSpThreads / 32) * G;
+    }
+    else
+    {
+        r_begin = ((long long)blockIdx.x * (kSpThreads / 32) + (threadIdx.x >> 5)) * RPW * RPG;
+        r_end = num_rows;
+        r_step = (long long)gridDim.x * (kSpThreads / TPR) * RPG;
+    }
+    for (long long r0 = r_begin; r0 < r_end; r0 += r_step)
     {
         int j[RPG], e[RPG];
         bool skip[RPG];
@@ -40,7 +57,7 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
         for (int g = 0; g < RPG; g++)
         {
             const long long r = r0 + g * RPW + sub;
-            const bool valid = x && r < num_rows;
+            const bool valid = x && r < r_end;
             const int s = valid ? ptr[row_start + r] : 0;
             e[g] = valid ? ptr[row_start + r + 1] : 0;
             skip[g] = e[g] - s > skip_len; // a listed long row: k_spmv_long owns it
@@ -82,7 +99,7 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
 #pragma unroll
             for (int o = TPR / 2; o > 0; o >>= 1) acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], o, TPR);
             const long long r = r0 + g * RPW + sub;
-            if (r < num_rows && lane == 0 && !skip[g]) epi(row_start + (int)r, acc[g]);
+            if (r < r_end && lane == 0 && !skip[g]) epi(row_start + (int)r, acc[g]);
         }
     }
 }
@@ -124,9 +141,138 @@ struct CsrView
     int num_rows, num_cols, num_nnz, threads_per_row;
     const int *long_rows;
     int num_long_rows, long_row_threshold;
+    const int *sell_off, *sell_col;
+    const VT *sell_val;
+    const int *sell_row;
+    int sell_num_slices, sell_lanes, sell_window;
 };
-static CsrView<double> view(const prfdd_csr_matrix &A) { return {A.ptr, A.col, A.val, A.num_rows, A.num_cols, A.num_nnz, A.threads_per_row, A.long_rows, A.num_long_rows, A.long_row_threshold}; }
-static CsrView<float> view(const prfdd_csr_matrix_f32 &A) { return {A.ptr, A.col, A.val, A.num_rows, A.num_cols, A.num_nnz, A.threads_per_row, A.long_rows, A.num_long_rows, A.long_row_threshold}; }
+static CsrView<double> view(const prfdd_csr_matrix &A) { return {A.ptr, A.col, A.val, A.num_rows, A.num_cols, A.num_nnz, A.threads_per_row, A.long_rows, A.num_long_rows, A.long_row_threshold, A.sell_off, A.sell_col, A.sell_val, A.sell_row, A.sell_num_slices, A.sell_lanes, A.sell_window}; }
+static CsrView<float> view(const prfdd_csr_matrix_f32 &A) { return {A.ptr, A.col, A.val, A.num_rows, A.num_cols, A.num_nnz, A.threads_per_row, A.long_rows, A.num_long_rows, A.long_row_threshold, A.sell_off, A.sell_col, A.sell_val, A.sell_row, A.sell_num_slices, A.sell_lanes, A.sell_window}; }
+
+// Sliced layout (prfdd_sell_layout): a warp owns one slice of 32/T slots; the walk over the slice is warp-uniform, every col / val
+// load of the warp is ONE contiguous line request, U chunks (col, val, then the gathers) are in flight per lane.  Lane t of a
+// row takes its entries t, t + T, ... in order and the lanes are combined by the same shuffle tree as in k_spmv<T>: same sums.
+// bulk prefetch of a contiguous global range into L2 (no destination register, no scoreboard entry): bytes a multiple of 16
+__device__ __forceinline__ void prefetch_l2(const void *p, int bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// Scheduling note (measured, profiles/r2_notes.txt): ptxas fits this loop into 32 registers and issues its loads as dependent
+// col/val -> x pairs; stating a larger budget in the launch bounds makes it issue U col / val loads and U gathers back to back
+// (40-53 registers), which is SLOWER here (level 1: 46 -> 50-56 us) -- the kernel is bound by L1 wavefronts (one per distinct
+// 128-byte line a warp load touches, ~2 cycles each), not by the latency of a warp's chain, and 64 resident warps hide that latency.
+template <int T, int U, bool PF, class VT, class Epi>
+__global__ void __launch_bounds__(kSpThreads) k_spmv_sell(const int *__restrict__ off, const int *__restrict__ scol, const VT *__restrict__ sval, const int *__restrict__ srow, const VT *__restrict__ x, int num_slices, int num_rows, Epi epi)
+{
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (kSpThreads / 32);
+    for (int s = blockIdx.x * (kSpThreads / 32) + (threadIdx.x >> 5); s < num_slices; s += nwarps)
+    {
+        // lanes 0 and 1 fetch the slice bounds in one request
+        const int o = off[s + (lane & 1)];
+        const int b = __shfl_sync(0xffffffffu, o, 0), e = __shfl_sync(0xffffffffu, o, 1);
+        if (PF && s + nwarps < num_slices)
+        {
+            // the warp's next slice is contiguous and known: bulk-prefetch it into L2 while this one is walked
+            const int on = off[s + nwarps + (lane & 1)];
+            const int bn = __shfl_sync(0xffffffffu, on, 0), en = __shfl_sync(0xffffffffu, on, 1);
+            if (lane == 0 && en > bn)
+            {
+                prefetch_l2(scol + bn, (en - bn) * 4);
+                prefetch_l2(sval + bn, (en - bn) * (int)sizeof(VT));
+            }
+        }
+        int row = -1;
+        if (lane % T == 0)
+        {
+            const int slot = s * (32 / T) + lane / T;
+            row = srow ? srow[slot] : (slot < num_rows ? slot : -1);
+        }
+        VT acc = VT(0);
+        for (int k = b + lane; k < e; k += 32 * U)
+        {
+            int c[U];
+            VT v[U];
+#pragma unroll
+            for (int i = 0; i < U; i++)
+            {
+                const bool on = k + 32 * i < e;
+                c[i] = on ? scol[k + 32 * i] : 0;
+                v[i] = on ? sval[k + 32 * i] : VT(0);
+            }
+#pragma unroll
+            for (int i = 0; i < U; i++)
+                if (k + 32 * i < e) acc += v[i] * x[c[i]];
+        }
+#pragma unroll
+        for (int o2 = T / 2; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2, T);
+        if (row >= 0) epi(row, acc);
+    }
+}
+
+// Sorted layout (sell_row set): the rows of a slice are scattered over their 256-row window, so row-indexed epilogue operands
+// (ds, r, f, the outputs) would cost a line request per row.  One CTA owns one window: its warps walk the window's slices (dealt
+// round robin: they are sorted by width), park the row sums in shared memory, and after one barrier thread t finishes row
+// w0 + t -- every epilogue access is contiguous again.  sell_row holds the row of each slot; only its offset in the window is used.
+template <int T, int U, class VT, class Epi>
+__global__ void __launch_bounds__(kSpThreads) k_spmv_sell_window(const int *__restrict__ off, const int *__restrict__ scol, const VT *__restrict__ sval, const int *__restrict__ srow, const VT *__restrict__ x, int num_slices, int num_rows, Epi epi)
+{
+    constexpr int R = 32 / T;          // rows per slice
+    constexpr int SPW = kSpThreads / R; // slices per window of kSpThreads rows
+    __shared__ VT ax[kSpThreads];
+    const int lane = threadIdx.x & 31;
+    const int w0 = blockIdx.x * kSpThreads;
+    for (int q = threadIdx.x >> 5; q < SPW; q += kSpThreads / 32)
+    {
+        const int s = blockIdx.x * SPW + q;
+        if (s >= num_slices) break; // warp-uniform
+        const int o = off[s + (lane & 1)];
+        const int b = __shfl_sync(0xffffffffu, o, 0), e = __shfl_sync(0xffffffffu, o, 1);
+        int row = -1;
+        if (lane % T == 0) row = srow[s * R + lane / T];
+        VT acc = VT(0);
+        for (int k = b + lane; k < e; k += 32 * U)
+        {
+            int c[U];
+            VT v[U];
+#pragma unroll
+            for (int i = 0; i < U; i++)
+            {
+                const bool on = k + 32 * i < e;
+                c[i] = on ? scol[k + 32 * i] : 0;
+                v[i] = on ? sval[k + 32 * i] : VT(0);
+            }
+#pragma unroll
+            for (int i = 0; i < U; i++)
+                if (k + 32 * i < e) acc += v[i] * x[c[i]];
+        }
+#pragma unroll
+        for (int o2 = T / 2; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2, T);
+        if (row >= 0) ax[row - w0] = acc;
+    }
+    __syncthreads();
+    const int row = w0 + threadIdx.x;
+    if (row < num_rows) epi(row, ax[threadIdx.x]);
+}
+
+template <int T, class VT, class Epi>
+static void launch_sell(const CsrView<VT> &A, const VT *x, cudaStream_t st, Epi epi)
+{
+    static const int waves = getenv("PRFDD_SELL_WAVES") ? atoi(getenv("PRFDD_SELL_WAVES")) : 8;
+    static const int unroll = getenv("PRFDD_SELL_UNROLL") ? atoi(getenv("PRFDD_SELL_UNROLL")) : 4;
+    const int grid = stream_grid(A.sell_num_slices, kSpThreads / 32, 1, waves);
+    static const bool pf = getenv("PRFDD_SELL_PREFETCH") != nullptr;
+    static const bool no_window = getenv("PRFDD_SELL_NO_WINDOW_KERNEL") != nullptr;
+    (void)unroll;
+    // sorted inside windows of kSpThreads rows (prfdd_sell_layout with window_rows = 256): CTA per window when that still fills the chip
+    // twice over and a warp has at most two slices to walk (measured on the c2 hierarchy: level-1 A 47.2 -> 44.5 us, R of level 0
+    // 27.4 -> 21.0 us; but 135 k rows x 8 lanes 29.6 -> 35.8 us, 18 k rows x 16 lanes 12.8 -> 43 us)
+    if (A.sell_row && A.sell_window == kSpThreads && T <= 2 && A.num_rows >= 2 * 8 * kSpThreads * num_sms() && !no_window)
+        k_spmv_sell_window<T, 4, VT><<<(A.num_rows + kSpThreads - 1) / kSpThreads, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
+    else if (pf) k_spmv_sell<T, 4, true, VT><<<grid, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
+    else k_spmv_sell<T, 4, false, VT><<<grid, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
+}
 
 template <int TPR, bool UNIT, class VT, class Epi>
 static void launch_spmv(const CsrView<VT> &A, const VT *x, int row_start, int num_rows, bool lr, cudaStream_t st, Epi epi)
@@ -134,10 +280,21 @@ static void launch_spmv(const CsrView<VT> &A, const VT *x, int row_start, int nu
     // two rows per sub-warp once the matrix is large enough to fill the machine with half as many warps
     // (AMG level 1 of the 16^3 N=7 problem, 27 entries/row: 54.9 -> 49.1 us; profiles/r1_notes.txt)
     const bool two = TPR >= 4 && (long long)num_rows * TPR >= (1ll << 21);
-    const int grid = stream_grid((long long)num_rows * TPR / (two ? 2 : 1), kSpThreads, 1, 16);
     const int skip_len = lr ? A.long_row_threshold : 0x7fffffff;
-    if (two) k_spmv<TPR, 2, UNIT, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
-    else k_spmv<TPR, 1, UNIT, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
+    static const int local_cps = getenv("PRFDD_SPMV_LOCAL") ? atoi(getenv("PRFDD_SPMV_LOCAL")) : 0; // experiment knob: CTAs per SM
+    static const long long local_min = getenv("PRFDD_SPMV_LOCAL_MIN") ? atoll(getenv("PRFDD_SPMV_LOCAL_MIN")) : 65536;
+    if (local_cps > 0 && x && num_rows >= local_min)
+    {
+        const int grid = num_sms() * local_cps;
+        if (two) k_spmv<TPR, 2, UNIT, true, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
+        else k_spmv<TPR, 1, UNIT, true, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
+    }
+    else
+    {
+        const int grid = stream_grid((long long)num_rows * TPR / (two ? 2 : 1), kSpThreads, 1, 16);
+        if (two) k_spmv<TPR, 2, UNIT, false, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
+        else k_spmv<TPR, 1, UNIT, false, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
+    }
     if (lr) k_spmv_long<UNIT, VT><<<(A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
 }
 
@@ -161,6 +318,20 @@ static int spmv(const CsrView<VT> &A, const VT *x, int row_start, int num_rows, 
         if (!x) return -8;
         if (unit) k_spmv_single<true, VT><<<stream_grid(num_rows, 256, 2, 8), 256, 0, st>>>(A.col, nullptr, x, row_start, num_rows, epi);
         else k_spmv_single<false, VT><<<stream_grid(num_rows, 256, 2, 8), 256, 0, st>>>(A.col, A.val, x, row_start, num_rows, epi);
+        return launched(bytes);
+    }
+    if (A.sell_col && x && !unit && row_start == 0 && num_rows == A.num_rows)
+    {
+        switch (A.sell_lanes)
+        {
+        case 1: launch_sell<1, VT>(A, x, st, epi); break;
+        case 2: launch_sell<2, VT>(A, x, st, epi); break;
+        case 4: launch_sell<4, VT>(A, x, st, epi); break;
+        case 8: launch_sell<8, VT>(A, x, st, epi); break;
+        case 16: launch_sell<16, VT>(A, x, st, epi); break;
+        case 32: launch_sell<32, VT>(A, x, st, epi); break;
+        default: return -6;
+        }
         return launched(bytes);
     }
     const int tpr = A.threads_per_row > 0 ? A.threads_per_row : 4;
@@ -362,6 +533,33 @@ __global__ void __launch_bounds__(256) k_dense_solve(double *__restrict__ x, con
 
 using namespace prfdd;
 
+template <class VT>
+static int sell_fill(const int *ptr, const int *col, const double *val, int num_rows, int lanes, const int *off, const int *slot_row, int *scol, VT *sval)
+{
+    if (!ptr || !col || !val || !off || !slot_row || !scol || !sval) return -8;
+    const int R = 32 / lanes;
+    const int num_slices = (num_rows + R - 1) / R;
+    for (int s = 0; s < num_slices; s++)
+    {
+        const int width = (off[s + 1] - off[s]) / 32;
+        for (int q = 0; q < R; q++)
+        {
+            const int r = slot_row[s * R + q];
+            const int b = r >= 0 ? ptr[r] : 0, len = r >= 0 ? ptr[r + 1] - ptr[r] : 0;
+            const int pad_col = len > 0 ? col[b + len - 1] : 0; // padding re-reads the row's last column: no new line is touched
+            for (int k = 0; k < width; k++)
+                for (int t = 0; t < lanes; t++)
+                {
+                    const int i = k * lanes + t;
+                    const size_t pos = (size_t)off[s] + 32 * (size_t)k + q * lanes + t;
+                    scol[pos] = i < len ? col[b + i] : pad_col;
+                    sval[pos] = i < len ? (VT)val[b + i] : VT(0);
+                }
+        }
+    }
+    return 0;
+}
+
 extern "C" {
 
 int prfdd_gather(double *nodes, const int *ptr, const int *col, const double *u, const double *weight, int num_nodes, prfdd_stream_t stream)
@@ -441,6 +639,46 @@ int prfdd_csr_plan(prfdd_csr_matrix *A, const int *ptr_host, int *long_rows_host
         A->long_row_threshold = threshold;
     }
     return listed;
+}
+
+long long prfdd_sell_layout(const int *ptr_host, int num_rows, int lanes, int window_rows, int *slice_off_host, int *slot_row_host)
+{
+    if (!ptr_host || !slice_off_host || !slot_row_host || num_rows < 0) return -8;
+    if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return -6;
+    const int R = 32 / lanes;
+    const int num_slices = (num_rows + R - 1) / R;
+    std::vector<int> order((size_t)num_rows);
+    for (int r = 0; r < num_rows; r++) order[r] = r;
+    auto chunks = [&](int r) { return (ptr_host[r + 1] - ptr_host[r] + lanes - 1) / lanes; };
+    if (window_rows > R)
+        for (int w0 = 0; w0 < num_rows; w0 += window_rows)
+            std::stable_sort(order.begin() + w0, order.begin() + std::min(num_rows, w0 + window_rows), [&](int a, int b) { return chunks(a) > chunks(b); });
+    long long total = 0;
+    slice_off_host[0] = 0;
+    for (int s = 0; s < num_slices; s++)
+    {
+        int width = 0;
+        for (int q = 0; q < R; q++)
+        {
+            const int slot = s * R + q;
+            const int r = slot < num_rows ? order[slot] : -1;
+            slot_row_host[slot] = r;
+            if (r >= 0) width = std::max(width, chunks(r));
+        }
+        total += 32ll * width;
+        if (total > 0x7fffffffll) return -9;
+        slice_off_host[s + 1] = (int)total;
+    }
+    return total;
+}
+
+int prfdd_sell_fill(const int *ptr_host, const int *col_host, const double *val_host, int num_rows, int lanes, const int *slice_off_host, const int *slot_row_host, int *sell_col_host, double *sell_val_host)
+{
+    return sell_fill(ptr_host, col_host, val_host, num_rows, lanes, slice_off_host, slot_row_host, sell_col_host, sell_val_host);
+}
+int prfdd_sell_fill_f32(const int *ptr_host, const int *col_host, const double *val_host, int num_rows, int lanes, const int *slice_off_host, const int *slot_row_host, int *sell_col_host, float *sell_val_host)
+{
+    return sell_fill(ptr_host, col_host, val_host, num_rows, lanes, slice_off_host, slot_row_host, sell_col_host, sell_val_host);
 }
 
 // ---- descriptor entry points ----------------------------------------------------------------

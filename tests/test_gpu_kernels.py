@@ -332,8 +332,23 @@ def test_csr_ragged_rows_and_row_ranges(G, tpr, nr):
 
 class CsrDesc(C.Structure):
     """prfdd_csr_matrix (include/prfdd_b200.h)"""
-    _fields_ = [("ptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p), ("num_rows", C.c_int), ("num_nnz", C.c_int), ("threads_per_row", C.c_int),
-                ("long_rows", C.c_void_p), ("num_long_rows", C.c_int), ("long_row_threshold", C.c_int)]
+    _fields_ = [("ptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p), ("num_rows", C.c_int), ("num_cols", C.c_int), ("num_nnz", C.c_int),
+                ("threads_per_row", C.c_int), ("long_rows", C.c_void_p), ("num_long_rows", C.c_int), ("long_row_threshold", C.c_int),
+                ("sell_off", C.c_void_p), ("sell_col", C.c_void_p), ("sell_val", C.c_void_p), ("sell_row", C.c_void_p),
+                ("sell_num_slices", C.c_int), ("sell_lanes", C.c_int), ("sell_window", C.c_int)]
+
+
+def test_descriptor_mirror_matches_the_header():
+    """the ctypes mirror above has the size the C compiler gives prfdd_csr_matrix"""
+    import os, subprocess, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "prfdd_b200.h"\nint main(void){ printf("%zu %zu %zu %zu", sizeof(prfdd_csr_matrix), offsetof(prfdd_csr_matrix, threads_per_row), offsetof(prfdd_csr_matrix, sell_off), offsetof(prfdd_csr_matrix, sell_window)); return 0; }\n'
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "a.out")
+        r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), "-x", "c", "-", "-o", exe], input=src, text=True, capture_output=True)
+        assert r.returncode == 0, r.stderr
+        got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
+    assert got == [C.sizeof(CsrDesc), CsrDesc.threads_per_row.offset, CsrDesc.sell_off.offset, CsrDesc.sell_window.offset]
 
 
 def csr_descriptor(G, ptr_host, dptr, dcol, dval, tpr=None):
@@ -352,6 +367,63 @@ def csr_descriptor(G, ptr_host, dptr, dcol, dval, tpr=None):
     if tpr is not None:
         D.threads_per_row = tpr
     return D, keep
+
+
+def sell_descriptor(G, D, ptr, col, val, lanes, window):
+    """adds the sliced copy (prfdd_sell_layout / prfdd_sell_fill) to descriptor D; returns the device arrays to keep alive"""
+    lib = G.lib
+    lib.prfdd_sell_layout.restype = C.c_longlong
+    nr = len(ptr) - 1
+    R = 32 // lanes
+    S = (nr + R - 1) // R
+    off = np.zeros(S + 1, np.int32); slot_row = np.zeros(S * R, np.int32)
+    total = lib.prfdd_sell_layout(P(ptr), C.c_int(nr), C.c_int(lanes), C.c_int(window), P(off), P(slot_row))
+    assert total >= ptr[-1]
+    scol = np.zeros(max(total, 1), np.int32); sval = np.zeros(max(total, 1))
+    assert lib.prfdd_sell_fill(P(ptr), P(col), P(val), C.c_int(nr), C.c_int(lanes), P(off), P(slot_row), P(scol), P(sval)) == 0
+    keep = [G.dev(off), G.dev(scol), G.dev(sval), G.dev(slot_row)]
+    D.sell_off, D.sell_col, D.sell_val = (k.data_ptr() for k in keep[:3])
+    D.sell_row = None if np.array_equal(slot_row[:nr], np.arange(nr)) else keep[3].data_ptr()
+    D.sell_num_slices, D.sell_lanes = S, lanes
+    D.sell_window = 0 if D.sell_row is None else window
+    return keep
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
+@pytest.mark.parametrize("window", [0, 64, 256])   # 256: the CTA-per-window kernel; 64: sorted, generic kernel
+def test_sliced_copy_gives_the_row_kernels_sums(G, lanes, window):
+    """the sliced (SELL) kernel with T lanes per row adds the entries of a row in the order of k_spmv<T>: identical results, for every
+    fused epilogue of the V-cycle, on ragged rows (empty rows, rows of several hundred entries)"""
+    rng = np.random.default_rng(7 * lanes + window)
+    lib = G.lib
+    nr = 5003; nc = 4000
+    lens = rng.integers(0, 30, nr); lens[rng.integers(0, nr, 25)] = rng.integers(100, 400, 25); lens[:2] = [0, 170]; lens[-1] = 0
+    ptr = np.zeros(nr + 1, np.int32); ptr[1:] = np.cumsum(lens)
+    col = np.concatenate([np.sort(rng.choice(nc, k, replace=False)) for k in lens]).astype(np.int32)
+    val = rng.standard_normal(ptr[-1])
+    x = rng.standard_normal(nc); f = rng.standard_normal(nr); ds = rng.uniform(0.5, 2.0, nr); r = rng.standard_normal(nr)
+    dptr, dcol, dval, dx, df, dds, dr = (G.dev(a) for a in (ptr, col, val, x, f, ds, r))
+    D, keep = csr_descriptor(G, ptr, dptr, dcol, dval, lanes)
+    D.long_rows, D.num_long_rows, D.long_row_threshold = None, 0, 0
+    Sd = CsrDesc.from_buffer_copy(D)
+    keep2 = sell_descriptor(G, Sd, ptr, col, val, lanes, window)
+    outs = []
+    for desc in (D, Sd):
+        y, v, rr, tt, u1, u2, t3, fr = (G.dev(np.full(nr, 3.0)) for _ in range(8))
+        assert lib.prfdd_csrm_multiply(G.p(y), C.byref(desc), G.p(dx), G.stream()) == 0
+        assert lib.prfdd_csrm_residual(G.p(v), C.byref(desc), G.p(dx), G.p(df), G.stream()) == 0
+        assert lib.prfdd_csrm_cheby_residual(G.p(rr), G.p(tt), C.byref(desc), G.p(dx), G.p(df), G.p(dds), C.c_double(0.3), G.stream()) == 0
+        assert lib.prfdd_csrm_cheby_step(G.p(u1), G.p(t3), C.byref(desc), G.p(dx), G.p(dr), G.p(dds), C.c_double(0.7), C.c_int(0), C.c_int(0), G.stream()) == 0
+        assert lib.prfdd_csrm_cheby_step(G.p(u2), None, C.byref(desc), G.p(dx), G.p(dr), G.p(dds), C.c_double(0.7), C.c_int(1), C.c_int(0), G.stream()) == 0
+        assert lib.prfdd_csrm_restrict_cheby_residual(G.p(fr), G.p(rr), G.p(tt), C.byref(desc), G.p(dx), G.p(dds), C.c_double(0.3), G.stream()) == 0
+        assert lib.prfdd_csrm_matvec(G.p(y), C.byref(desc), G.p(dx), C.c_double(1.0), C.c_double(1.0), G.stream()) == 0
+        G.sync()
+        outs.append([G.host(a) for a in (y, v, rr, tt, u1, u2, t3, fr)])
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((val, col, ptr), shape=(nr, nc))
+    assert np.abs(outs[1][1] - (f - A @ x)).max() <= 1e-13 * (np.abs(A) @ np.abs(x)).max()
 
 
 @pytest.mark.parametrize("tpr", [1, 2, 4, 8])
