@@ -150,7 +150,8 @@ typedef struct prfdd_csr_matrix
     const int *sell_off;    /* [sell_num_slices + 1] first entry of each slice, multiples of 32 */
     const int *sell_col;    /* [sell_off[sell_num_slices]] */
     const double *sell_val;
-    const int *sell_row;    /* [sell_num_slices * 32 / sell_lanes] row of each slot, -1: none; NULL: slot = row */
+    const int *sell_row;    /* [sell_num_slices * 32 / sell_lanes] row of each slot, -1: none; NULL: slot = row.  Rows on the
+                             * long_rows list must NOT be in the sliced copy (slot row -1): they get their warp-per-row launch */
     int sell_num_slices;
     int sell_lanes;         /* lanes per row: 1, 2, 4, 8, 16 or 32 */
     int sell_window;        /* window_rows the layout was sorted with (0: row order); 256 selects the CTA-per-window kernel */

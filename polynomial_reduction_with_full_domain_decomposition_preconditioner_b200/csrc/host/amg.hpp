@@ -727,7 +727,7 @@ struct DeviceCSR
     void build_sell(const HostCSR &A, bool fp32)
     {
         static const int enabled = getenv("PRFDD_SELL") ? atoi(getenv("PRFDD_SELL")) : 1;
-        static const int min_rows = getenv("PRFDD_SELL_MIN_ROWS") ? atoi(getenv("PRFDD_SELL_MIN_ROWS")) : 8192;
+        static const int min_rows = getenv("PRFDD_SELL_MIN_ROWS") ? atoi(getenv("PRFDD_SELL_MIN_ROWS")) : 256;
         static const int window = getenv("PRFDD_SELL_WINDOW") ? atoi(getenv("PRFDD_SELL_WINDOW")) : 256;
         static const int force_lanes = getenv("PRFDD_SELL_LANES") ? atoi(getenv("PRFDD_SELL_LANES")) : 0;
         static const bool verbose = getenv("PRFDD_SELL_VERBOSE") != nullptr;
@@ -736,17 +736,56 @@ struct DeviceCSR
         // ~20-entry rows 2, ~60-entry rows 8; small matrices with long rows 16 (they are latency bound: more slices)
         const double avg = (double)nnz / num_rows;
         int lanes = avg <= 10.0 ? 1 : avg <= 32.0 ? 2 : avg <= 48.0 ? 4 : 8;
-        while (lanes < 32 && lanes < avg / 4 && (long long)num_rows * lanes / 32 < 148 * 32) lanes *= 2; // a slice per warp: enough of them to fill the chip
+        // a slice per warp: enough of them to fill the chip; the longest row sets the length of a small launch, so it gets the lanes
+        int longest = 0;
+        for (int r = 0; r < num_rows; r++) longest = std::max(longest, A.ptr[r + 1] - A.ptr[r]);
+        while (lanes < 32 && (lanes < avg / 4 || lanes < longest / 16) && (long long)num_rows * lanes / 32 < 148 * 32) lanes *= 2;
         if (force_lanes > 0) lanes = force_lanes;
         const int R = 32 / lanes;
         const int num_slices = (num_rows + R - 1) / R;
         std::vector<int> off((size_t)num_slices + 1), slot_row((size_t)num_slices * R);
+        // Rows on the long-row list (hanging-node rows of the composite grid: 30-98 entries among 7-entry rows) stay with the warp-per-row
+        // launch: the sliced copy holds them as empty rows with slot row -1, so the other rows keep their order (sorting such a
+        // matrix by length scatters the rows of a slice over the window and costs more gather lines than the padding it saves:
+        // 2-rank level-0 A 47.7 us with the row kernels, 59.8 us sorted, measured)
+        const bool hybrid = desc.num_long_rows > 0 && desc.long_row_threshold > 0;
+        static const bool keep_hybrid = getenv("PRFDD_SELL_HYBRID") != nullptr;
+        if (hybrid && !keep_hybrid) return; // measured: the row kernels + long-row launch win on these (2-rank level-0 A 47.7 us; sliced 50-55 us either way)
+        HostCSR B; // A without its long rows
+        if (hybrid)
+        {
+            B.num_rows = num_rows; B.num_cols = num_cols;
+            B.ptr.assign((size_t)num_rows + 1, 0);
+            for (int r = 0; r < num_rows; r++)
+            {
+                const int len = A.ptr[r + 1] - A.ptr[r];
+                B.ptr[r + 1] = B.ptr[r] + (len > desc.long_row_threshold ? 0 : len);
+            }
+            B.col.resize((size_t)B.ptr[num_rows]); B.val.resize((size_t)B.ptr[num_rows]);
+            for (int r = 0; r < num_rows; r++)
+                if (B.ptr[r + 1] > B.ptr[r])
+                {
+                    std::copy(A.col.begin() + A.ptr[r], A.col.begin() + A.ptr[r + 1], B.col.begin() + B.ptr[r]);
+                    std::copy(A.val.begin() + A.ptr[r], A.val.begin() + A.ptr[r + 1], B.val.begin() + B.ptr[r]);
+                }
+        }
+        const HostCSR &M = hybrid ? B : A;
+        const long long stored = M.ptr[num_rows];
         // row order when it pads little (no slot -> row list, contiguous epilogue accesses); else rows sorted by length in windows
-        long long total = prfdd_sell_layout(A.ptr.data(), num_rows, lanes, 0, off.data(), slot_row.data());
-        if (total < 0 || (double)total > 1.03 * nnz) total = prfdd_sell_layout(A.ptr.data(), num_rows, lanes, window, off.data(), slot_row.data());
+        long long total = prfdd_sell_layout(M.ptr.data(), num_rows, lanes, 0, off.data(), slot_row.data());
+        static const double row_order_tol = getenv("PRFDD_SELL_ROW_ORDER_TOL") ? atof(getenv("PRFDD_SELL_ROW_ORDER_TOL")) : 1.03;
+        const long long total_row_order = total;
+        if (total < 0 || (double)total > row_order_tol * stored) total = prfdd_sell_layout(M.ptr.data(), num_rows, lanes, window, off.data(), slot_row.data());
         if (total < 0) return; // too large for 32-bit offsets: the row kernels stay
         bool identity = true;
         for (int q = 0; q < num_rows && identity; q++) identity = slot_row[q] == q;
+        const bool row_order = identity;
+        if (hybrid)
+        {
+            for (size_t q = 0; q < slot_row.size(); q++)
+                if (slot_row[q] >= 0 && A.ptr[slot_row[q] + 1] - A.ptr[slot_row[q]] > desc.long_row_threshold) slot_row[q] = -1;
+            identity = false; // the slot -> row list carries the -1 marks
+        }
         std::vector<int> scol((size_t)std::max(total, 1ll));
         sell_off = prfdd_host::device.malloc<int>(num_slices + 1);
         sell_off.copyFrom(off.data(), (num_slices + 1) * sizeof(int));
@@ -754,7 +793,7 @@ struct DeviceCSR
         if (fp32)
         {
             std::vector<float> sval((size_t)std::max(total, 1ll));
-            prfdd_sell_fill_f32(A.ptr.data(), A.col.data(), A.val.data(), num_rows, lanes, off.data(), slot_row.data(), scol.data(), sval.data());
+            prfdd_sell_fill_f32(M.ptr.data(), M.col.data(), M.val.data(), num_rows, lanes, off.data(), slot_row.data(), scol.data(), sval.data());
             sell_val = prfdd_host::device.malloc<float>(std::max(total, 1ll));
             sell_val.copyFrom(sval.data(), total * sizeof(float));
             desc32.sell_val = sell_val.as<float>();
@@ -762,7 +801,7 @@ struct DeviceCSR
         else
         {
             std::vector<double> sval((size_t)std::max(total, 1ll));
-            prfdd_sell_fill(A.ptr.data(), A.col.data(), A.val.data(), num_rows, lanes, off.data(), slot_row.data(), scol.data(), sval.data());
+            prfdd_sell_fill(M.ptr.data(), M.col.data(), M.val.data(), num_rows, lanes, off.data(), slot_row.data(), scol.data(), sval.data());
             sell_val = prfdd_host::device.malloc<double>(std::max(total, 1ll));
             sell_val.copyFrom(sval.data(), total * sizeof(double));
             desc.sell_val = sell_val.as<double>();
@@ -778,10 +817,11 @@ struct DeviceCSR
         desc.sell_row = desc32.sell_row = identity ? nullptr : sell_row.as<int>();
         desc.sell_num_slices = desc32.sell_num_slices = num_slices;
         desc.sell_lanes = desc32.sell_lanes = lanes;
-        desc.sell_window = desc32.sell_window = identity ? 0 : window;
+        desc.sell_window = desc32.sell_window = (row_order || hybrid) ? 0 : window; // the CTA-per-window kernel needs every row of the window in the copy
+        if (verbose) fprintf(stderr, "sell: row order would pad %+.1f %%; ", 100.0 * (total_row_order - stored) / std::max(stored, 1ll));
         if (verbose)
             fprintf(stderr, "sell: %d x %d, %d entries (%.1f/row), lanes %d, window %d, %d slices, padded %lld (+%.1f %%), %s order\n", num_rows, num_cols, nnz,
-                    (double)nnz / num_rows, lanes, window, num_slices, total, 100.0 * (total - nnz) / nnz, identity ? "row" : "sorted");
+                    (double)nnz / num_rows, lanes, window, num_slices, total, 100.0 * (total - stored) / std::max(stored, 1ll), hybrid ? (row_order ? "row order, long rows apart" : "sorted, long rows apart") : row_order ? "row" : "sorted");
     }
 };
 

@@ -211,6 +211,58 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv_sell(const int *__restrict_
     }
 }
 
+// Few slices (a wave or two of warps: the coarse AMG levels and their R / P): such a launch lasts as long as one warp's dependent
+// chain, so here the loads of a trip ARE issued back to back -- plain pointer bumps, immediate offsets and a stated register
+// budget make ptxas keep U col / val loads and then U gathers in flight (see the scheduling note above).  Same sums, same order.
+template <int T, int U, class VT, class Epi>
+__global__ void __launch_bounds__(kSpThreads, 4) k_spmv_sell_small(const int *__restrict__ off, const int *__restrict__ scol, const VT *__restrict__ sval, const int *__restrict__ srow, const VT *__restrict__ x, int num_slices, int num_rows, Epi epi)
+{
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (kSpThreads / 32);
+    for (int s = blockIdx.x * (kSpThreads / 32) + (threadIdx.x >> 5); s < num_slices; s += nwarps)
+    {
+        const int o = off[s + (lane & 1)];
+        const int b = __shfl_sync(0xffffffffu, o, 0), e = __shfl_sync(0xffffffffu, o, 1);
+        int row = -1;
+        if (lane % T == 0)
+        {
+            const int slot = s * (32 / T) + lane / T;
+            row = srow ? srow[slot] : (slot < num_rows ? slot : -1);
+        }
+        VT acc = VT(0);
+        const int *cp = scol + b + lane;
+        const VT *vp = sval + b + lane;
+        int n = (e - b) >> 5;
+        while (n >= U)
+        {
+            int c[U];
+            VT v[U], xv[U];
+#pragma unroll
+            for (int i = 0; i < U; i++) { c[i] = cp[32 * i]; v[i] = vp[32 * i]; }
+#pragma unroll
+            for (int i = 0; i < U; i++) xv[i] = x[c[i]];
+#pragma unroll
+            for (int i = 0; i < U; i++) acc += v[i] * xv[i];
+            cp += 32 * U; vp += 32 * U; n -= U;
+        }
+        if (n > 0)
+        {
+            // the partial trip re-reads the lane's last chunk for the slots past the slice and adds it with value 0
+            int c[U];
+            VT v[U], xv[U];
+#pragma unroll
+            for (int i = 0; i < U - 1; i++) { const int q = i < n ? i : n - 1; c[i] = cp[32 * q]; v[i] = vp[32 * q]; }
+#pragma unroll
+            for (int i = 0; i < U - 1; i++) xv[i] = x[c[i]];
+#pragma unroll
+            for (int i = 0; i < U - 1; i++) acc += (i < n ? v[i] : VT(0)) * xv[i];
+        }
+#pragma unroll
+        for (int o2 = T / 2; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2, T);
+        if (row >= 0) epi(row, acc);
+    }
+}
+
 // Sorted layout (sell_row set): the rows of a slice are scattered over their 256-row window, so row-indexed epilogue operands
 // (ds, r, f, the outputs) would cost a line request per row.  One CTA owns one window: its warps walk the window's slices (dealt
 // round robin: they are sorted by width), park the row sums in shared memory, and after one barrier thread t finishes row
@@ -264,12 +316,15 @@ static void launch_sell(const CsrView<VT> &A, const VT *x, cudaStream_t st, Epi 
     const int grid = stream_grid(A.sell_num_slices, kSpThreads / 32, 1, waves);
     static const bool pf = getenv("PRFDD_SELL_PREFETCH") != nullptr;
     static const bool no_window = getenv("PRFDD_SELL_NO_WINDOW_KERNEL") != nullptr;
+    static const bool no_small = getenv("PRFDD_SELL_NO_SMALL_KERNEL") != nullptr;
     (void)unroll;
     // sorted inside windows of kSpThreads rows (prfdd_sell_layout with window_rows = 256): CTA per window when that still fills the chip
     // twice over and a warp has at most two slices to walk (measured on the c2 hierarchy: level-1 A 47.2 -> 44.5 us, R of level 0
     // 27.4 -> 21.0 us; but 135 k rows x 8 lanes 29.6 -> 35.8 us, 18 k rows x 16 lanes 12.8 -> 43 us)
     if (A.sell_row && A.sell_window == kSpThreads && T <= 2 && A.num_rows >= 2 * 8 * kSpThreads * num_sms() && !no_window)
         k_spmv_sell_window<T, 4, VT><<<(A.num_rows + kSpThreads - 1) / kSpThreads, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
+    else if (A.sell_num_slices <= 4 * (kSpThreads / 32) * num_sms() && !no_small) // half a wave of warps (measured: at a full wave the plain kernel is as fast or faster)
+        k_spmv_sell_small<T, 4, VT><<<grid, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
     else if (pf) k_spmv_sell<T, 4, true, VT><<<grid, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
     else k_spmv_sell<T, 4, false, VT><<<grid, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
 }
@@ -331,6 +386,12 @@ static int spmv(const CsrView<VT> &A, const VT *x, int row_start, int num_rows, 
         case 16: launch_sell<16, VT>(A, x, st, epi); break;
         case 32: launch_sell<32, VT>(A, x, st, epi); break;
         default: return -6;
+        }
+        if (A.num_long_rows > 0 && A.long_rows)
+        {
+            // the listed rows are not in the sliced copy (slot row -1): warp per row from the CSR arrays, as after the row kernels
+            k_spmv_long<false, VT><<<(A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
+            prfdd_launch_count_add(1);
         }
         return launched(bytes);
     }
