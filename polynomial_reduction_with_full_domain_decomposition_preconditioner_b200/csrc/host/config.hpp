@@ -45,5 +45,18 @@ inline void setup_mark(const char *what)
     last = now;
 }
 
+// nested stopwatch for the stages inside one mark (own clock, so that the outer marks still measure whole stages)
+inline void setup_submark(const char *what)
+{
+    static const bool on = getenv("PRFDD_SETUP_TIMING") != nullptr;
+    static double last = -1.0;
+    if (!on || prfdd_host::proc_id != 0) return;
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec + 1e-9 * ts.tv_nsec;
+    if (last >= 0.0 && what) fprintf(stderr, "[setup]     . %-40s %7.2f s\n", what, now - last);
+    last = now;
+}
+
 #define rstdout(...) { if (prfdd_host::proc_id == 0 && prfdd_host::verbose) { printf(__VA_ARGS__); fflush(stdout); } }
 #define pstdout(...) { if (prfdd_host::pstdout_file) { fprintf(prfdd_host::pstdout_file, __VA_ARGS__); fflush(prfdd_host::pstdout_file); } }

@@ -179,6 +179,7 @@ void Domain<DType>::initialize(const char *directory_, int poly_degree_, bool so
     using namespace prfdd_host;
     directory = directory_;
     poly_degree = poly_degree_;
+    setup_submark(nullptr);
 
     char file_name[4096];
     auto path = [&](const char *name) {
@@ -266,6 +267,7 @@ void Domain<DType>::initialize(const char *directory_, int poly_degree_, bool so
         throw std::runtime_error("ERROR: There was a problem reading Nek5000 data in " + directory);
     }
 
+    setup_submark("read mesh files, upload geometry");
     // Communication (tpp:233-284)
     if (proc_id == 0 && verbose) printf("Setting up domain stitching handle...\n");
 
@@ -296,7 +298,9 @@ void Domain<DType>::initialize(const char *directory_, int poly_degree_, bool so
                 count++;
             }
 
+    setup_submark("node numbering (boundary first, first touch)");
     setup_halo(); // stands where gslib_gs_setup stands (tpp:283-284)
+    setup_submark("halo lists");
 
     // Q, Qt (tpp:286-294)
     num_local_nodes = (int)local_node_degree.size();
@@ -306,6 +310,7 @@ void Domain<DType>::initialize(const char *directory_, int poly_degree_, bool so
         for (int v = 0; v < elem.num_points; v++) Q.add_entry(elem.loc_num[v], local_node_idx[elem.glo_num[v]], 1.0);
     Q.assemble();
     Q.transpose(Qt);
+    setup_submark("Q, Qt");
 
     // total number of unique nodes = sum over ranks and nodes of 1/multiplicity... counted exactly with integers below
     // assembled_weight = 1 / (Qt 1 (+) gs_add)  (tpp:296-302)
@@ -358,6 +363,7 @@ void Domain<DType>::initialize(const char *directory_, int poly_degree_, bool so
         z_k = device.malloc<DType>(P);
         p_k = device.malloc<DType>(P);
     }
+    setup_submark("weights, node count, buffers");
     H.assign(num_vectors, std::vector<DType>(num_vectors));
     c_gmres.assign(num_vectors, 0);
     s_gmres.assign(num_vectors, 0);

@@ -24,30 +24,15 @@ constexpr int kSpThreads = 256;
 // (rows r, r + 32/TPR, ...), which multiplies the independent col/val -> x load chains a lane has in
 // flight; the long rows of the coarse AMG levels are latency bound without it.
 // VT: value type of the matrix, the gathered vector and the row sums (double; float for the FP32 V-cycle, AMG/config.hpp:4)
-// LOCAL: every CTA walks ONE contiguous slice of the rows (grid = resident CTAs of the whole chip), so the rows an SM works on
-// stay neighbours for the whole launch and the gathers of x entries shared by neighbouring rows hit that SM's L1 instead of
-// being fetched from L2 once per SM that happens to hold one of the rows (the grid-stride form sweeps one chip-wide front).
-template <int TPR, int RPG, bool UNIT, bool LOCAL, class VT, class Epi>
+template <int TPR, int RPG, bool UNIT, class VT, class Epi>
 __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr, const int *__restrict__ col, const VT *__restrict__ val, const VT *__restrict__ x, int row_start, int num_rows, int skip_len, Epi epi)
 {
     constexpr int RPW = 32 / TPR; // rows per warp and pass
     const int lane = threadIdx.x % TPR;
     const int sub = (threadIdx.x & 31) / TPR;
-    long long r_begin, r_end, r_step;
-    if constexpr (LOCAL)
-    {
-        constexpr int G = RPW * RPG; // rows of one warp pass: slices start on a multiple of it
-        const long long slice = ((num_rows + (long long)gridDim.x * G - 1) / ((long long)gridDim.x * G)) * G;
-        r_begin = blockIdx.x * slice + (threadIdx.x >> 5) * G;
-        r_end = (blockIdx.x + 1) * slice < num_rows ? (blockIdx.x + 1) * slice : num_rows;
-        r_step = (kSpThreads / 32) * G;
-    }
-    else
-    {
-        r_begin = ((long long)blockIdx.x * (kSpThreads / 32) + (threadIdx.x >> 5)) * RPW * RPG;
-        r_end = num_rows;
-        r_step = (long long)gridDim.x * (kSpThreads / TPR) * RPG;
-    }
+    const long long r_begin = ((long long)blockIdx.x * (kSpThreads / 32) + (threadIdx.x >> 5)) * RPW * RPG;
+    const long long r_end = num_rows;
+    const long long r_step = (long long)gridDim.x * (kSpThreads / TPR) * RPG;
     for (long long r0 = r_begin; r0 < r_end; r0 += r_step)
     {
         int j[RPG], e[RPG];
@@ -152,17 +137,11 @@ static CsrView<float> view(const prfdd_csr_matrix_f32 &A) { return {A.ptr, A.col
 // Sliced layout (prfdd_sell_layout): a warp owns one slice of 32/T slots; the walk over the slice is warp-uniform, every col / val
 // load of the warp is ONE contiguous line request, U chunks (col, val, then the gathers) are in flight per lane.  Lane t of a
 // row takes its entries t, t + T, ... in order and the lanes are combined by the same shuffle tree as in k_spmv<T>: same sums.
-// bulk prefetch of a contiguous global range into L2 (no destination register, no scoreboard entry): bytes a multiple of 16
-__device__ __forceinline__ void prefetch_l2(const void *p, int bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 // Scheduling note (measured, profiles/r2_notes.txt): ptxas fits this loop into 32 registers and issues its loads as dependent
 // col/val -> x pairs; stating a larger budget in the launch bounds makes it issue U col / val loads and U gathers back to back
 // (40-53 registers), which is SLOWER here (level 1: 46 -> 50-56 us) -- the kernel is bound by L1 wavefronts (one per distinct
 // 128-byte line a warp load touches, ~2 cycles each), not by the latency of a warp's chain, and 64 resident warps hide that latency.
-template <int T, int U, bool PF, class VT, class Epi>
+template <int T, int U, class VT, class Epi>
 __global__ void __launch_bounds__(kSpThreads) k_spmv_sell(const int *__restrict__ off, const int *__restrict__ scol, const VT *__restrict__ sval, const int *__restrict__ srow, const VT *__restrict__ x, int num_slices, int num_rows, Epi epi)
 {
     const int lane = threadIdx.x & 31;
@@ -172,17 +151,6 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv_sell(const int *__restrict_
         // lanes 0 and 1 fetch the slice bounds in one request
         const int o = off[s + (lane & 1)];
         const int b = __shfl_sync(0xffffffffu, o, 0), e = __shfl_sync(0xffffffffu, o, 1);
-        if (PF && s + nwarps < num_slices)
-        {
-            // the warp's next slice is contiguous and known: bulk-prefetch it into L2 while this one is walked
-            const int on = off[s + nwarps + (lane & 1)];
-            const int bn = __shfl_sync(0xffffffffu, on, 0), en = __shfl_sync(0xffffffffu, on, 1);
-            if (lane == 0 && en > bn)
-            {
-                prefetch_l2(scol + bn, (en - bn) * 4);
-                prefetch_l2(sval + bn, (en - bn) * (int)sizeof(VT));
-            }
-        }
         int row = -1;
         if (lane % T == 0)
         {
@@ -312,12 +280,9 @@ template <int T, class VT, class Epi>
 static void launch_sell(const CsrView<VT> &A, const VT *x, cudaStream_t st, Epi epi)
 {
     static const int waves = getenv("PRFDD_SELL_WAVES") ? atoi(getenv("PRFDD_SELL_WAVES")) : 8;
-    static const int unroll = getenv("PRFDD_SELL_UNROLL") ? atoi(getenv("PRFDD_SELL_UNROLL")) : 4;
     const int grid = stream_grid(A.sell_num_slices, kSpThreads / 32, 1, waves);
-    static const bool pf = getenv("PRFDD_SELL_PREFETCH") != nullptr;
     static const bool no_window = getenv("PRFDD_SELL_NO_WINDOW_KERNEL") != nullptr;
     static const bool no_small = getenv("PRFDD_SELL_NO_SMALL_KERNEL") != nullptr;
-    (void)unroll;
     // sorted inside windows of kSpThreads rows (prfdd_sell_layout with window_rows = 256): CTA per window when that still fills the chip
     // twice over and a warp has at most two slices to walk (measured on the c2 hierarchy: level-1 A 47.2 -> 44.5 us, R of level 0
     // 27.4 -> 21.0 us; but 135 k rows x 8 lanes 29.6 -> 35.8 us, 18 k rows x 16 lanes 12.8 -> 43 us)
@@ -325,8 +290,8 @@ static void launch_sell(const CsrView<VT> &A, const VT *x, cudaStream_t st, Epi 
         k_spmv_sell_window<T, 4, VT><<<(A.num_rows + kSpThreads - 1) / kSpThreads, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
     else if (A.sell_num_slices <= 4 * (kSpThreads / 32) * num_sms() && !no_small) // half a wave of warps (measured: at a full wave the plain kernel is as fast or faster)
         k_spmv_sell_small<T, 4, VT><<<grid, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
-    else if (pf) k_spmv_sell<T, 4, true, VT><<<grid, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
-    else k_spmv_sell<T, 4, false, VT><<<grid, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
+    else
+        k_spmv_sell<T, 4, VT><<<grid, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
 }
 
 template <int TPR, bool UNIT, class VT, class Epi>
@@ -336,20 +301,9 @@ static void launch_spmv(const CsrView<VT> &A, const VT *x, int row_start, int nu
     // (AMG level 1 of the 16^3 N=7 problem, 27 entries/row: 54.9 -> 49.1 us; profiles/r1_notes.txt)
     const bool two = TPR >= 4 && (long long)num_rows * TPR >= (1ll << 21);
     const int skip_len = lr ? A.long_row_threshold : 0x7fffffff;
-    static const int local_cps = getenv("PRFDD_SPMV_LOCAL") ? atoi(getenv("PRFDD_SPMV_LOCAL")) : 0; // experiment knob: CTAs per SM
-    static const long long local_min = getenv("PRFDD_SPMV_LOCAL_MIN") ? atoll(getenv("PRFDD_SPMV_LOCAL_MIN")) : 65536;
-    if (local_cps > 0 && x && num_rows >= local_min)
-    {
-        const int grid = num_sms() * local_cps;
-        if (two) k_spmv<TPR, 2, UNIT, true, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
-        else k_spmv<TPR, 1, UNIT, true, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
-    }
-    else
-    {
-        const int grid = stream_grid((long long)num_rows * TPR / (two ? 2 : 1), kSpThreads, 1, 16);
-        if (two) k_spmv<TPR, 2, UNIT, false, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
-        else k_spmv<TPR, 1, UNIT, false, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
-    }
+    const int grid = stream_grid((long long)num_rows * TPR / (two ? 2 : 1), kSpThreads, 1, 16);
+    if (two) k_spmv<TPR, 2, UNIT, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
+    else k_spmv<TPR, 1, UNIT, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
     if (lr) k_spmv_long<UNIT, VT><<<(A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
 }
 

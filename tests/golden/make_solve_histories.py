@@ -16,7 +16,15 @@ CASES = [  # dim, nel, N, r, eps, ranks, outer solver (0 FCG / 1 GMRES)
     (3, 2, 9, 3, 0.03, 1, 0), (2, 8, 4, 3, 0.04, 2, 0), (3, 4, 3, 2, 0.04, 2, 0),   # the 2-rank cases are those of tests/test_gpu_multi.py
 ]
 
+# `python make_solve_histories.py dim nel N r eps ranks solver` computes ONE extra case and adds it to the file (the 8-rank c4 case
+# takes the oracle many minutes: tests/multi_gpu_check.py --golden-only compares an 8-GPU run with it without re-running the oracle)
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "solve_histories.json")
+EXTRA = [(3, 8, 9, 3, 0.03, 8, 0)]   # BASELINE configs[3] (c4) on 8 ranks: 2x2x2 blocks of 4^3 elements, ladder 9/6/3/1
 out = []
+if len(sys.argv) == 8:
+    a = sys.argv[1:]
+    CASES = [(int(a[0]), int(a[1]), int(a[2]), int(a[3]), float(a[4]), int(a[5]), int(a[6]))]
+    out = [c for c in json.load(open(OUT)) if (c["dim"], c["nel"], c["N"], c["r"], c["eps"], c["ranks"], c["solver"]) != CASES[0]]
 for dim, nel, N, r, eps, ranks, solver in CASES:
     d = tempfile.mkdtemp()
     for n in subdomain.ladder(N, r):
@@ -28,4 +36,4 @@ for dim, nel, N, r, eps, ranks, solver in CASES:
     out.append(dict(dim=dim, nel=nel, N=N, r=r, eps=eps, ranks=ranks, solver=solver, iterations=int(W.num_iterations),
                     history=[float(h) for h in W.history]))
     print(out[-1]["dim"], nel, N, r, ranks, solver, "->", W.num_iterations, "iterations")
-json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "solve_histories.json"), "w"), indent=1)
+json.dump(out, open(OUT, "w"), indent=1)

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--degree", dest="N", type=int, default=5)
     ap.add_argument("--reduction", dest="r", type=int, default=2)
     ap.add_argument("--eps", type=float, default=0.04)
+    ap.add_argument("--golden-only", action="store_true", help="compare with tests/golden/solve_histories.json only (no oracle run on the GPU box)")
     a = ap.parse_args()
     a.nel = tuple(int(x) for x in a.nel.split(",")) if "," in a.nel else int(a.nel)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -54,7 +55,19 @@ def main():
                                  nw=S.get_array("NORM_WEIGHT"), iw=S.get_array("INNER_WEIGHT")))
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
-        if rank == 0:
+        if rank == 0 and a.golden_only:
+            import json
+            gold = [c for c in json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solve_histories.json")))
+                    if (c["dim"], c["nel"], c["N"], c["r"], c["eps"], c["ranks"], c["solver"]) == (a.dim, list(a.nel) if isinstance(a.nel, tuple) else a.nel, a.N, a.r, a.eps, world, solver_id)]
+            if solver_id == 0:
+                assert gold, "no golden record for this case"
+            for c in gold:
+                ref = np.array(c["history"])
+                assert gathered[0]["nit"] == c["iterations"], (gathered[0]["nit"], c["iterations"])
+                assert np.abs(gathered[0]["hist"] - ref).max() <= 1e-9 * ref[0], np.abs(gathered[0]["hist"] - ref).max() / ref[0]
+                print("solver_id %d: GPU iters %d = golden (oracle, build container) iters %d, max history diff / r0 %.2e, final relative residual %.2e"
+                      % (solver_id, gathered[0]["nit"], c["iterations"], np.abs(gathered[0]["hist"] - ref).max() / ref[0], gathered[0]["hist"][-1] / gathered[0]["hist"][0]), flush=True)
+        elif rank == 0:
             from oracle import domain as od
             W = od.DomainWorld(d, a.N, world)
             Sd = None
