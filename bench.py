@@ -319,7 +319,7 @@ def operator_roofline(pr, torch, stream, peaks, peaks_kind):
     t_ms = float(np.mean(times))
     bytes_alg = 64.0 * P                                  # u 8 + six G 48 + Au 8 per point
     achieved = bytes_alg / (t_ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "k_ax3d_bulk<8> (prfdd_stiffness_matrix_hd, 4096 elements, n=8)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    return {"bound": "hbm", "kernel": "%s (prfdd_stiffness_matrix_hd, %d elements, n=%d)" % ("k_ax3d_bulk<8>" if n == 8 else "k_ax3d_bulk<6>" if n == 6 else "k_ax3d_big<%d>" % n if n > 10 else "k_ax3d<%d>" % n, E, n), "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"], "traffic": operator_traffic(E, n), "peak_source": peaks_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peaks_kind == "measured" else "fallback 6.65 TB/s",
             "avg_launch_ms": t_ms, "algorithmic_bytes_per_launch": bytes_alg}
 
@@ -344,8 +344,13 @@ def main():
     ap.add_argument("--eps", type=float, default=0.0, help="mesh deformation (the reference's profiling meshes are Kershaw eps = 0.3, profile.sh:5-11)")
     ap.add_argument("--coarsening", default="hmis", choices=["hmis", "pmis"])
     ap.add_argument("--amg-precision", default="double", choices=["double", "float"], help="float: the FP32 V-cycle (`Float float`, AMG/config.hpp:4; SURVEY 8f N3); the headline runs double")
+    ap.add_argument("--degree", type=int, default=7, help="polynomial degree N (headline: 7); other values are extra records (configs[3], configs[4]), not the headline")
+    ap.add_argument("--reduction", type=int, default=3, help="degree reduction per ladder step (headline: 3 -> ladder 7, 4, 1)")
+    ap.add_argument("--nel-per-gpu", type=int, default=16, help="elements per side of a rank's block in weak scaling (headline: 16)")
     ap.add_argument("--phases", action="store_true", help="add the fenced per-phase table (reference Timer keys) of one extra solve")
     args = ap.parse_args()
+    global N_DEG, REDUCTION, NEL_PER_GPU
+    N_DEG, REDUCTION, NEL_PER_GPU = args.degree, args.reduction, args.nel_per_gpu
     if args.impl == "reference":
         return run_reference(args)
     if args.warmup < 3:
@@ -525,8 +530,9 @@ def main():
             cpu = cpu_baseline(args.cpu_nel)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "3D SEM Poisson, %dx%dx%d hex box mesh, N=7, FP64, PR-FDD preconditioned flexible CG (ladder 7/4/1, overlaps 1/1, inner GMRES(4), 1 V-cycle, Chebyshev order 2)" % tuple(nel)
-                           if use_pc else "3D SEM Poisson, %dx%dx%d hex box mesh, N=7, FP64, flexible CG WITHOUT the PR-FDD preconditioner (PRFDD_BENCH_NO_PC set)" % tuple(nel),
+                "config": {"workload": "3D SEM Poisson, %dx%dx%d hex box mesh, N=%d, FP64, PR-FDD preconditioned flexible CG (ladder %s, overlaps 1/1, inner GMRES(4), 1 V-cycle, Chebyshev order 2)"
+                           % (tuple(nel) + (N_DEG, "/".join(str(x) for x in pr.ladder(N_DEG, REDUCTION))))
+                           if use_pc else "3D SEM Poisson, %dx%dx%d hex box mesh, N=%d, FP64, flexible CG WITHOUT the PR-FDD preconditioner (PRFDD_BENCH_NO_PC set)" % (tuple(nel) + (N_DEG,)),
                            "tolerance": TOL, "global_nodes": nodes, "iterations_per_solve": iters // args.steps, "l2": "working set (geometry 96 MiB + vectors + AMG hierarchy) exceeds the 126 MB L2",
                            "partition": "%dx%dx%d blocks of %dx%dx%d elements" % (tuple(P3) + tuple(n // p for n, p in zip(nel, P3))), "mesh_deformation_eps": args.eps,
                            "amg_coarsening": args.coarsening, "amg_precision": args.amg_precision, "time_to_solution_ms": ms / args.steps, "setup_s": setup_s, "mesh_generation_s": mesh_s, "rel_error_vs_exact": err,
