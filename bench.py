@@ -514,7 +514,7 @@ def main():
             o = (C.c_double * 6)()
             if L.prfdd_solver_time_spmv(S.h, C.c_int(40), o) == 0:
                 ach = o[1] / (o[0] * 1e-3) / 1e9
-                roof = {"bound": "hbm", "kernel": "k_spmv<TPR,RPG> + Chebyshev epilogue (prfdd_csrm_cheby_step) on AMG levels 0 and 1 of the low-order FEM hierarchy, alternating "
+                roof = {"bound": "hbm", "kernel": "sliced SpMV (k_spmv_sell / k_spmv_sell_window) + Chebyshev epilogue (prfdd_csrm_cheby_step) on AMG levels 0 and 1 of the low-order FEM hierarchy, alternating "
                         "(level 0: %d rows, %d nnz; level 1: %d rows, %d nnz) -- the SpMV family is the dominant kernel of the solve (profiles/)" % (o[2], o[3], o[4], o[5]),
                         "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic(o),
                         "peak_source": roof_op["peak_source"], "avg_launch_ms": o[0], "algorithmic_bytes_per_launch": o[1],
