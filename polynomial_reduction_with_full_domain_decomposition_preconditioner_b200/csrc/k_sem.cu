@@ -239,8 +239,9 @@ __global__ void __launch_bounds__(N *N, MINB) k_ax3d_bulk(double *__restrict__ A
 }
 
 // large degrees (n > 10): D stays in shared memory, everything else identical
+// two resident CTAs for n >= 15 (128 registers): n = 16 94.8 -> 74.2 us per 512 elements (measured)
 template <int N>
-__global__ void __launch_bounds__(N *N) k_ax3d_big(double *__restrict__ Au, const double *__restrict__ u, const G6 G, const double *__restrict__ Dg, long long first_point, int num_elems)
+__global__ void __launch_bounds__(N *N, (N >= 15 ? 2 : 1)) k_ax3d_big(double *__restrict__ Au, const double *__restrict__ u, const G6 G, const double *__restrict__ Dg, long long first_point, int num_elems)
 {
     constexpr int N2 = N * N, N3 = N * N * N;
     constexpr int LD = N + 1;
@@ -306,6 +307,169 @@ __global__ void __launch_bounds__(N *N) k_ax3d_big(double *__restrict__ Au, cons
 
 #pragma unroll
     for (int k = 0; k < N; k++) Au[base + k * N2] = r_Au[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// n = 16 (degree 15, BASELINE configs[4]) on the FP64 tensor cores.  k_ax3d_big<16> is bound by shared-memory wavefronts (ncu:
+// data-pipe wavefronts 76 % of peak, FP64 pipe 22 %, 0.28 of the HBM roofline): every multiply-add of the five contractions
+// reads one or two operands from shared memory.  The contractions of one element are 96 products of 16x16 matrices
+// (per k plane  Ur = U_k D^T, Us = D U_k;  per j plane  Ut = D T_j;  and the three transposed ones), so here they run as
+// mma.sync.m8n8k4.f64: one shared-memory read per operand FRAGMENT (256 multiply-adds) instead of per multiply-add, D and D^T
+// fragments in registers.  One element per CTA of 8 warps; warp w owns the k planes 2w, 2w+1 for the r/s products and the
+// j planes 2w, 2w+1 for the t products; ut / gt cross between the two ownerships through shared memory (two block barriers),
+// G is read once, in accumulator layout (pairs of points), straight from global memory.
+// Measured (512 elements, 134 MB): 94.8 us (k_ax3d_big, one CTA per SM) -> 74.2 us (two CTAs) -> 41.8 us = 0.50 of the HBM roofline; a bulk L2
+// prefetch of the element's factor blocks (46.9 us) and a register pipeline of the G reads (43.6 us) did not help and are not kept.
+//   fragments (lane l, g = l/4, t = l%4):  A(tm,ks) = X[8tm+g][4ks+t],  B(ks,tn) = Y[4ks+t][8tn+g],  C(tm,tn) = Z[8tm+g][8tn+2t+{0,1}]
+// Shared layout  i + 20 j + 324 k: both strides are 4 mod 16, so that the 16 lanes of a half warp of every fragment read
+// (4 rows x 4 columns) hit 16 different 8-byte banks.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 2) k_ax3d_mma16(double *__restrict__ Au, const double *__restrict__ u, const G6 G, const double *__restrict__ Dg, long long first_point)
+{
+    constexpr int N = 16, N2 = 256, N3 = 4096, SJ = 20, SK = 324, PLANE = 16 * SJ;
+    extern __shared__ __align__(16) double sm[];
+    double *U = sm;                 // u, then per k plane: gr, then the r+s part of Au
+    double *W = sm + N * SK;        // ut, then gt
+    double *GS = sm + 2 * N * SK;   // per warp: one plane of gs
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const long long ebase = first_point + (long long)blockIdx.x * N3;
+    auto idx = [](int i, int j, int k) { return i + j * SJ + k * SK; };
+
+    // D fragments: DA[tm][ks] = D[8tm+g][4ks+t]  (D as A operand, D^T as B operand);  DB[ks][tn] = D[4ks+t][8tn+g]  (D as B operand, D^T as A operand)
+    double DA[2][4], DB[4][2];
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++)
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+        {
+            DA[q][ks] = Dg[(8 * q + g) * N + 4 * ks + t];
+            DB[ks][q] = Dg[(4 * ks + t) * N + 8 * q + g];
+        }
+    // the element's u
+#pragma unroll
+    for (int r = 0; r < 16; r++)
+    {
+        const int p = tid + 256 * r;
+        U[idx(p & 15, (p >> 4) & 15, r)] = u[ebase + p];
+    }
+    __syncthreads();
+
+    // t products: ut(.,j,.) = D T_j,  T_j[m][i] = u(i,j,m)
+#pragma unroll 1
+    for (int jj = 0; jj < 2; jj++)
+    {
+        const int j = 2 * w + jj;
+        double C[2][2][2] = {};
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++)
+#pragma unroll
+            for (int tn = 0; tn < 2; tn++)
+            {
+                const double b = U[idx(8 * tn + g, j, 4 * ks + t)];
+                dmma(C[0][tn], DA[0][ks], b);
+                dmma(C[1][tn], DA[1][ks], b);
+            }
+#pragma unroll
+        for (int tm = 0; tm < 2; tm++)
+#pragma unroll
+            for (int tn = 0; tn < 2; tn++) *reinterpret_cast<double2 *>(&W[idx(8 * tn + 2 * t, j, 8 * tm + g)]) = make_double2(C[tm][tn][0], C[tm][tn][1]);
+    }
+    __syncthreads();
+
+    // r and s products of the warp's k planes, the geometric factors, and the transposed r and s products
+    double *gsb = GS + w * PLANE;
+#pragma unroll 1
+    for (int kk = 0; kk < 2; kk++)
+    {
+        const int k = 2 * w + kk;
+        double CR[2][2][2] = {}, CS[2][2][2] = {};
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++)
+        {
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+            {
+                const double a = U[idx(4 * ks + t, 8 * q + g, k)]; // U_k[j][m] as A(tm = q)
+                dmma(CR[q][0], a, DA[0][ks]);
+                dmma(CR[q][1], a, DA[1][ks]);
+                const double b = U[idx(8 * q + g, 4 * ks + t, k)]; // U_k[m][i] as B(tn = q)
+                dmma(CS[0][q], DA[0][ks], b);
+                dmma(CS[1][q], DA[1][ks], b);
+            }
+        }
+        __syncwarp(); // every fragment of U_k has been read: the plane is overwritten below
+#pragma unroll
+        for (int tm = 0; tm < 2; tm++)
+#pragma unroll
+            for (int tn = 0; tn < 2; tn++)
+            {
+                const int i0 = 8 * tn + 2 * t, j = 8 * tm + g;
+                const int o = idx(i0, j, k);
+                const double2 ut = *reinterpret_cast<const double2 *>(&W[o]);
+                const long long p = ebase + i0 + N * j + N2 * k;
+                const double2 g0 = *reinterpret_cast<const double2 *>(&G.g[0][p]), g1 = *reinterpret_cast<const double2 *>(&G.g[1][p]),
+                              g2 = *reinterpret_cast<const double2 *>(&G.g[2][p]), g3 = *reinterpret_cast<const double2 *>(&G.g[3][p]),
+                              g4 = *reinterpret_cast<const double2 *>(&G.g[4][p]), g5 = *reinterpret_cast<const double2 *>(&G.g[5][p]);
+                const double ur0 = CR[tm][tn][0], ur1 = CR[tm][tn][1], us0 = CS[tm][tn][0], us1 = CS[tm][tn][1];
+                *reinterpret_cast<double2 *>(&U[o]) = make_double2(g0.x * ur0 + g3.x * us0 + g4.x * ut.x, g0.y * ur1 + g3.y * us1 + g4.y * ut.y);
+                *reinterpret_cast<double2 *>(&gsb[i0 + j * SJ]) = make_double2(g3.x * ur0 + g1.x * us0 + g5.x * ut.x, g3.y * ur1 + g1.y * us1 + g5.y * ut.y);
+                *reinterpret_cast<double2 *>(&W[o]) = make_double2(g4.x * ur0 + g5.x * us0 + g2.x * ut.x, g4.y * ur1 + g5.y * us1 + g2.y * ut.y);
+            }
+        __syncwarp();
+        double CP[2][2][2] = {};
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++)
+        {
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+            {
+                const double a = U[idx(4 * ks + t, 8 * q + g, k)]; // Gr_k[j][m] as A(tm = q):  sum_m gr(m,j) D[m][i]
+                dmma(CP[q][0], a, DB[ks][0]);
+                dmma(CP[q][1], a, DB[ks][1]);
+                const double b = gsb[(4 * ks + t) * SJ + 8 * q + g]; // Gs_k[m][i] as B(tn = q):  sum_m D[m][j] gs(i,m)
+                dmma(CP[0][q], DB[ks][0], b);
+                dmma(CP[1][q], DB[ks][1], b);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int tm = 0; tm < 2; tm++)
+#pragma unroll
+            for (int tn = 0; tn < 2; tn++) *reinterpret_cast<double2 *>(&U[idx(8 * tn + 2 * t, 8 * tm + g, k)]) = make_double2(CP[tm][tn][0], CP[tm][tn][1]);
+    }
+    __syncthreads();
+
+    // transposed t products of the warp's j planes:  sum_m D[m][k] gt(i,j,m), plus the r+s part, to global memory
+#pragma unroll 1
+    for (int jj = 0; jj < 2; jj++)
+    {
+        const int j = 2 * w + jj;
+        double C[2][2][2] = {};
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++)
+#pragma unroll
+            for (int tn = 0; tn < 2; tn++)
+            {
+                const double b = W[idx(8 * tn + g, j, 4 * ks + t)];
+                dmma(C[0][tn], DB[ks][0], b);
+                dmma(C[1][tn], DB[ks][1], b);
+            }
+#pragma unroll
+        for (int tm = 0; tm < 2; tm++)
+#pragma unroll
+            for (int tn = 0; tn < 2; tn++)
+            {
+                const int i0 = 8 * tn + 2 * t, k = 8 * tm + g;
+                const double2 rs = *reinterpret_cast<const double2 *>(&U[idx(i0, j, k)]);
+                *reinterpret_cast<double2 *>(&Au[ebase + i0 + N * j + N2 * k]) = make_double2(C[tm][tn][0] + rs.x, C[tm][tn][1] + rs.y);
+            }
+    }
 }
 
 // 2D: one thread per point
@@ -387,6 +551,21 @@ static int launch_ax3d(double *Au, const double *u, const G6 &G, const double *D
     }
     else
     {
+        if constexpr (N == 16)
+        {
+            // tensor-core variant: pairs of points are read and written as 16-byte accesses
+            static const bool no_mma = getenv("PRFDD_AX_NO_MMA") != nullptr;
+            uintptr_t align = reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(Au);
+            for (int c = 0; c < 6; c++) align |= reinterpret_cast<uintptr_t>(G.g[c]);
+            if (!no_mma && first_point % 2 == 0 && align % 16 == 0)
+            {
+                constexpr int smem = (2 * 16 * 324 + 8 * 16 * 20) * (int)sizeof(double);
+                static const cudaError_t attr = cudaFuncSetAttribute(k_ax3d_mma16, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                if (attr != cudaSuccess) return (int)attr;
+                k_ax3d_mma16<<<num_elems, 256, smem, st>>>(Au, u, G, D_dev, first_point);
+                return launched(64.0 * num_elems * N * N * N);
+            }
+        }
         k_ax3d_big<N><<<num_elems, N * N, 0, st>>>(Au, u, G, D_dev, first_point, num_elems);
     }
     return launched(64.0 * num_elems * N * N * N); // u 8 + six factors 48 + Au 8 per point
