@@ -532,8 +532,16 @@ int prfdd_solver_profile_vcycle(prfdd_solver *s, int reps, char *text, int capac
  * element-major points, n = points per direction. */
 int prfdd_write_vtk(const char *path, int dim, int n, int num_elements, const double *x, const double *y, const double *z, int num_fields,
                     const char *const *field_names, const double *const *fields);
+/* the same for elements of different degrees: element e has n_of_element[e] points per side (Subdomain::output, subdomain.tpp:4648-4791) */
+int prfdd_write_vtk_mixed(const char *path, int dim, int num_elements, const int *n_of_element, const double *x, const double *y, const double *z,
+                          int num_fields, const char *const *field_names, const double *const *fields);
 /* poisson.cpp:233-235: u_star, f, u of this rank's elements -> <output_name>_<rank>.vtk */
 int prfdd_solver_output(prfdd_solver *s, const char *output_name);
+/* Subdomain::output (subdomain.tpp:4648-4791; never called by the reference's driver): this rank's subdomain region -- own elements
+ * at degree N, rings at the ladder degrees, extended N = 1 elements -- as low-order cells with the node fields "degree" (the
+ * element's polynomial degree), "f" (the composite right-hand side of the last preconditioner application) and "u" (its
+ * solution) -> <output_name>_<rank>.vtk */
+int prfdd_solver_output_subdomain(prfdd_solver *s, const char *output_name);
 /* timer report (Timer keys of timer.tpp / poisson.cpp:253-401): seconds for `key`, <0 if unknown */
 double prfdd_solver_timer_total(prfdd_solver *s, const char *key);
 

@@ -434,6 +434,14 @@ int prfdd_solver_output(prfdd_solver *s, const char *output_name)
     });
 }
 
+int prfdd_solver_output_subdomain(prfdd_solver *s, const char *output_name)
+{
+    return guarded(s, [&]() {
+        if (!s->subdomain || !s->opt.use_preconditioner) return -8;
+        return s->subdomain->output_last_application(output_name);
+    });
+}
+
 double prfdd_solver_timer_total(prfdd_solver *s, const char *key)
 {
     if (!strcmp(key, "__enable__")) { s->tmr.enabled = true; return 0.0; }

@@ -91,23 +91,40 @@ int prfdd_stream_synchronize(prfdd_stream_t s) { return (int)cudaStreamSynchroni
 int prfdd_write_vtk(const char *path, int dim, int n, int num_elements, const double *x, const double *y, const double *z, int num_fields,
                     const char *const *field_names, const double *const *fields)
 {
-    if (!path || (dim != 2 && dim != 3) || n < 2 || num_elements < 0 || !x || !y || (dim == 3 && !z)) return -8;
+    if (n < 2 || num_elements < 0) return -8;
+    std::vector<int> ns((size_t)std::max(num_elements, 1), n);
+    return prfdd_write_vtk_mixed(path, dim, num_elements, ns.data(), x, y, z, num_fields, field_names, fields);
+}
+
+// the same for elements of different degrees (a subdomain region: own elements at N, rings at the ladder degrees, extended N = 1
+// elements; Subdomain::output, subdomain.tpp:4648-4791): element e has n_of_element[e] points per side, points element-major
+int prfdd_write_vtk_mixed(const char *path, int dim, int num_elements, const int *n_of_element, const double *x, const double *y, const double *z,
+                          int num_fields, const char *const *field_names, const double *const *fields)
+{
+    if (!path || (dim != 2 && dim != 3) || num_elements < 0 || (num_elements > 0 && !n_of_element) || !x || !y || (dim == 3 && !z)) return -8;
+    long long num_points = 0, num_cells = 0;
+    for (int e = 0; e < num_elements; e++)
+    {
+        const long long n = n_of_element[e];
+        if (n < 2) return -8;
+        num_points += (dim == 2) ? n * n : n * n * n;
+        num_cells += (dim == 2) ? (n - 1) * (n - 1) : (n - 1) * (n - 1) * (n - 1);
+    }
     FILE *f = fopen(path, "w");
     if (!f) return -2;
-    const long long npe = (dim == 2) ? (long long)n * n : (long long)n * n * n;
-    const long long num_points = npe * num_elements;
     const int nv = (dim == 2) ? 4 : 8;
-    const long long cells_per_elem = (dim == 2) ? (long long)(n - 1) * (n - 1) : (long long)(n - 1) * (n - 1) * (n - 1);
-    const long long num_cells = cells_per_elem * num_elements;
     fprintf(f, "# vtk DataFile Version 3.0\nField data\nASCII\nDATASET UNSTRUCTURED_GRID\nPOINTS %lld double\n", num_points);
     for (long long p = 0; p < num_points; p++) fprintf(f, "%.17g %.17g %.17g\n", x[p], y[p], dim == 3 ? z[p] : 0.0);
     fprintf(f, "CELLS %lld %lld\n", num_cells, num_cells * (nv + 1));
+    long long element_offset = 0;
     for (int e = 0; e < num_elements; e++)
+    {
+        const int n = n_of_element[e];
         for (int sz = 0; sz < (dim == 3 ? n - 1 : 1); sz++)
             for (int sy = 0; sy < n - 1; sy++)
                 for (int sx = 0; sx < n - 1; sx++)
                 {
-                    const long long b = e * npe + sx + (long long)sy * n + (long long)sz * n * n;
+                    const long long b = element_offset + sx + (long long)sy * n + (long long)sz * n * n;
                     if (dim == 2) fprintf(f, "4 %lld %lld %lld %lld\n", b, b + 1, b + 1 + n, b + n);
                     else
                     {
@@ -115,6 +132,8 @@ int prfdd_write_vtk(const char *path, int dim, int n, int num_elements, const do
                         fprintf(f, "8 %lld %lld %lld %lld %lld %lld %lld %lld\n", b, b + 1, b + 1 + n, b + n, t, t + 1, t + 1 + n, t + n);
                     }
                 }
+        element_offset += (dim == 2) ? (long long)n * n : (long long)n * n * n;
+    }
     fprintf(f, "CELL_TYPES %lld\n", num_cells);
     for (long long c = 0; c < num_cells; c++) fprintf(f, dim == 2 ? "9\n" : "12\n");
     if (num_fields > 0) fprintf(f, "POINT_DATA %lld\n", num_points);

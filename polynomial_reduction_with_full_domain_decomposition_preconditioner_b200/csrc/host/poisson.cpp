@@ -2,6 +2,7 @@
 //   poisson <directory> <polynomial degree> <polynomial reduction> <subdomain overlap> <superdomain overlap> [solver_id]
 // (/root/reference/poisson.cpp:40-81, 150-251).  Single process = single GPU; multi-GPU runs are launched one process
 // per GPU with PRFDD_RANK / PRFDD_NRANKS / PRFDD_NCCL_ID_FILE in the environment (rank 0 writes the ncclUniqueId file).
+#include <string>
 #include "../../../include/prfdd_b200.h"
 #include <cstdio>
 #include <cstdlib>
@@ -93,6 +94,11 @@ int main(int argc, char *argv[])
     {
         rc = prfdd_solver_output(s, getenv("PRFDD_OUTPUT"));
         if (rc) { printf("ERROR: %s\n", prfdd_error_string(rc)); return EXIT_FAILURE; }
+        if (opt.use_preconditioner) // Subdomain::output (subdomain.tpp:4648-4791): the rank's region -> <name>_subdomain_<rank>.vtk
+        {
+            rc = prfdd_solver_output_subdomain(s, (std::string(getenv("PRFDD_OUTPUT")) + "_subdomain").c_str());
+            if (rc) { printf("ERROR: %s\n", prfdd_error_string(rc)); return EXIT_FAILURE; }
+        }
     }
     if (opt.proc_id == 0)
     {

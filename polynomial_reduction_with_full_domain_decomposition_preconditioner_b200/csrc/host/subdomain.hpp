@@ -228,6 +228,10 @@ class Subdomain
     void flexible_conjugate_gradient(memory &u_l, memory &f_l, bool print_history = true, bool use_relative = false);
     void generalized_minimum_residual(memory &u_l, memory &f_l, bool print_history = true, bool use_relative = false);
 
+    // subdomain.tpp:4648-4791: region mesh (elements of the ladder degrees as low-order cells) + node fields, legacy VTK instead of Silo
+    int output(const std::string &output_name, const std::vector<std::pair<std::string, const memory *>> &fields);
+    int output_last_application(const std::string &output_name) { return output(output_name, {{"f", &f}, {"u", &u_k}}); } // composite right-hand side and solution of the last inner solve
+
     // C ABI support
     long long query(int what);
     long long get_array(int what, void *dst, long long cap);
@@ -1266,6 +1270,53 @@ long long Subdomain<DType>::query(int what)
     }
     default: return -1;
     }
+}
+
+template <typename DType>
+int Subdomain<DType>::output(const std::string &output_name, const std::vector<std::pair<std::string, const memory *>> &fields)
+{
+    // element-major points of the region in the order of `elements` (tpp:4666-4668); a field lives in the region's point numbering:
+    // work_hst[1][elem.offset + v] = field[elem.loc_num[v]] (tpp:4779-4781)
+    long long num_points = 0;
+    for (auto &elem : elements) num_points += elem.num_points;
+    std::vector<int> n_of((size_t)elements.size());
+    std::vector<double> x((size_t)num_points), y((size_t)num_points), z((size_t)num_points), degree((size_t)num_points);
+    std::vector<long long> off(elements.size() + 1, 0);
+    for (size_t e = 0; e < elements.size(); e++)
+    {
+        const auto &elem = elements[e];
+        n_of[e] = elem.poly_degree + 1;
+        off[e + 1] = off[e] + elem.num_points;
+        for (int v = 0; v < elem.num_points; v++)
+        {
+            x[off[e] + v] = elem.x[v];
+            y[off[e] + v] = elem.y.empty() ? 0.0 : elem.y[v];
+            z[off[e] + v] = elem.z.empty() ? 0.0 : elem.z[v];
+            degree[off[e] + v] = elem.poly_degree;
+        }
+    }
+    std::vector<std::vector<double>> data(fields.size());
+    std::vector<const char *> names{"degree"};
+    std::vector<const double *> ptrs{degree.data()};
+    std::vector<double> raw;
+    for (size_t k = 0; k < fields.size(); k++)
+    {
+        const long long have = (long long)(fields[k].second->size() / sizeof(DType));
+        raw.assign((size_t)have, 0.0);
+        fields[k].second->copyTo(raw.data(), (size_t)have * sizeof(DType));
+        data[k].assign((size_t)num_points, 0.0);
+        for (size_t e = 0; e < elements.size(); e++)
+            for (int v = 0; v < elements[e].num_points; v++)
+            {
+                const long long src = elements[e].loc_num[v];
+                if (src >= 0 && src < have) data[k][off[e] + v] = raw[src];
+            }
+        names.push_back(fields[k].first.c_str());
+        ptrs.push_back(data[k].data());
+    }
+    char path[1024];
+    snprintf(path, sizeof(path), "%s_%d.vtk", output_name.c_str(), prfdd_host::proc_id);
+    return prfdd_write_vtk_mixed(path, prfdd_host::dim, (int)elements.size(), n_of.data(), x.data(), y.data(), z.data(), (int)names.size(), names.data(), ptrs.data());
 }
 
 template <typename DType>

@@ -46,6 +46,14 @@ def test_poisson_driver(prfdd, tmp_path, solver_id):
     assert "DATASET UNSTRUCTURED_GRID" in head and "POINTS %d double" % (27 * 125) in head
     text = open(os.path.join(d, "domain_0.vtk")).read()
     assert "CELLS %d %d" % (27 * 64, 27 * 64 * 9) in text and all(("SCALARS %s double 1" % k) in text for k in ("u_star", "f", "u"))
+    # Subdomain::output (subdomain.tpp:4648-4791): the rank's region; on one rank = the 27 own elements at degree 4, fields degree / f / u
+    sub = open(os.path.join(d, "domain_subdomain_0.vtk")).read()
+    assert "POINTS %d double" % (27 * 125) in sub and "CELLS %d %d" % (27 * 64, 27 * 64 * 9) in sub
+    assert all(("SCALARS %s double 1" % k) in sub for k in ("degree", "f", "u"))
+    vals = sub.split("SCALARS degree double 1\nLOOKUP_TABLE default\n")[1].split("SCALARS")[0].split()
+    assert len(vals) == 27 * 125 and set(vals) == {"4"}
+    uvals = [float(v) for v in sub.split("SCALARS u double 1\nLOOKUP_TABLE default\n")[1].split()]
+    assert len(uvals) == 27 * 125 and any(abs(v) > 0 for v in uvals)
 
 
 def test_usage_message():

@@ -61,3 +61,35 @@ def test_vtk_writer(prfdd, tmp_path, dim, nel, N):
             assert vol > 0
     assert L.prfdd_write_vtk(b"/nonexistent_dir/x.vtk", C.c_int(dim), C.c_int(n), C.c_int(E), vp(x), vp(y), vp(z), C.c_int(0), None, None) == -2
     assert L.prfdd_write_vtk(path.encode(), C.c_int(4), C.c_int(n), C.c_int(E), vp(x), vp(y), vp(z), C.c_int(0), None, None) == -8
+
+
+def test_vtk_writer_mixed_degrees(prfdd, tmp_path):
+    """prfdd_write_vtk_mixed: elements of different degrees in one file (the region mesh of Subdomain::output, subdomain.tpp:4648-4791)"""
+    L = prfdd.lib()
+    dim = 3
+    ns = np.array([4, 2, 3], np.int32)                        # points per side of the three elements
+    pts = []
+    for e, n in enumerate(ns):
+        g = np.linspace(0.0, 1.0, n)
+        X, Y, Z = np.meshgrid(g + 1.1 * e, g, g, indexing="ij")
+        pts.append(np.stack([X.transpose(2, 1, 0).ravel(), Y.transpose(2, 1, 0).ravel(), Z.transpose(2, 1, 0).ravel()], 1))   # i fastest
+    P = np.concatenate(pts)
+    x, y, z = (np.ascontiguousarray(P[:, k]) for k in range(3))
+    fld = x + 2 * y + 3 * z
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    names = (C.c_char_p * 1)(b"lin")
+    fields = (C.c_void_p * 1)(fld.ctypes.data)
+    path = str(tmp_path / "mixed.vtk")
+    assert L.prfdd_write_vtk_mixed(path.encode(), C.c_int(dim), C.c_int(3), vp(ns), vp(x), vp(y), vp(z), C.c_int(1), names, fields) == 0
+    got, cells, types, f = _parse(path)
+    assert got.shape == (int((ns.astype(np.int64) ** 3).sum()), 3) and np.array_equal(got, P)
+    assert len(cells) == int(((ns - 1).astype(np.int64) ** 3).sum()) and set(types) == {12}
+    assert np.array_equal(f["lin"], fld)
+    # first cell of the second element starts at that element's offset and uses ITS points per side
+    c = cells[27]
+    o, n = 64, 2
+    assert c[1:] == [o, o + 1, o + 1 + n, o + n, o + n * n, o + n * n + 1, o + n * n + 1 + n, o + n * n + n]
+    for c in cells:
+        p = got[c[1:]]
+        assert np.linalg.det(np.stack([p[1] - p[0], p[3] - p[0], p[4] - p[0]])) > 0
+    assert L.prfdd_write_vtk_mixed(path.encode(), C.c_int(dim), C.c_int(3), vp(np.array([4, 1, 3], np.int32)), vp(x), vp(y), vp(z), C.c_int(0), None, None) == -8
