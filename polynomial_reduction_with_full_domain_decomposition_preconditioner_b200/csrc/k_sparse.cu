@@ -457,14 +457,24 @@ static int t_cheby_step(VT *u, VT *t_out, const CsrView<VT> &A, const VT *t_in, 
 
 // dense x = M b for both value types (k_dense_solve above is the double instance)
 template <class VT>
-__global__ void __launch_bounds__(256) k_dense_t(VT *__restrict__ x, const VT *__restrict__ M, const VT *__restrict__ b, int n)
+__global__ void __launch_bounds__(256, 4) k_dense_t(VT *__restrict__ x, const VT *__restrict__ M, const VT *__restrict__ b, int n)
 {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= n) return; // whole warps leave together
     const VT *__restrict__ row = M + (size_t)r * n;
-    VT acc = VT(0);
-    for (int c = lane; c < n; c += 32) acc += row[c] * b[c];
+    // four independent partial sums per lane: the eight loads of a trip are in flight together (the matrix is L2 resident, the
+    // launch is one wave: its length is one warp's chain)
+    VT a0 = VT(0), a1 = VT(0), a2 = VT(0), a3 = VT(0);
+    int c = lane;
+    for (; c + 96 < n; c += 128)
+    {
+        const VT m0 = row[c], m1 = row[c + 32], m2 = row[c + 64], m3 = row[c + 96];
+        const VT b0 = b[c], b1 = b[c + 32], b2 = b[c + 64], b3 = b[c + 96];
+        a0 += m0 * b0; a1 += m1 * b1; a2 += m2 * b2; a3 += m3 * b3;
+    }
+    for (; c < n; c += 32) a0 += row[c] * b[c];
+    VT acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) x[r] = acc;
@@ -532,14 +542,23 @@ __global__ void __launch_bounds__(256) k_scatter_assign(double *__restrict__ dst
 
 // dense x = M b, one warp per row, lanes stride through the row (coalesced), fixed-order shuffle sum.  Serves the coarsest-level
 // inverse (a handful of rows) and the collapsed coarse levels of the V-cycle (a couple of thousand rows, amg.hpp).
-__global__ void __launch_bounds__(256) k_dense_solve(double *__restrict__ x, const double *__restrict__ Ainv, const double *__restrict__ b, int n)
+__global__ void __launch_bounds__(256, 4) k_dense_solve(double *__restrict__ x, const double *__restrict__ Ainv, const double *__restrict__ b, int n)
 {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= n) return; // whole warps leave together
     const double *__restrict__ row = Ainv + (size_t)r * n;
-    double acc = 0.0;
-    for (int c = lane; c < n; c += 32) acc += row[c] * b[c];
+    // four independent partial sums per lane (see k_dense_t)
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int c = lane;
+    for (; c + 96 < n; c += 128)
+    {
+        const double m0 = row[c], m1 = row[c + 32], m2 = row[c + 64], m3 = row[c + 96];
+        const double b0 = b[c], b1 = b[c + 32], b2 = b[c + 64], b3 = b[c + 96];
+        a0 += m0 * b0; a1 += m1 * b1; a2 += m2 * b2; a3 += m3 * b3;
+    }
+    for (; c < n; c += 32) a0 += row[c] * b[c];
+    double acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) x[r] = acc;

@@ -72,16 +72,27 @@ __device__ __forceinline__ void block_sum(double (&acc)[K], double *smem /* [K][
     __syncthreads();
 }
 
+// two elements per trip with their own partial sums (the operand loads of both are independent and in flight together; a register
+// budget is stated because ptxas otherwise fits the loop into 32 registers by serialising them, profiles/r2_notes.txt); the two
+// partial sums are added in a fixed order
 template <int K, class F>
-__global__ void __launch_bounds__(kRedThreads) k_reduce(long long n, F f, double *partials, unsigned int *counter, double *out, int out_stride)
+__global__ void __launch_bounds__(kRedThreads, 4) k_reduce(long long n, F f, double *partials, unsigned int *counter, double *out, int out_stride)
 {
     __shared__ double smem[K * (kRedThreads / 32)];
     __shared__ bool is_last;
-    double acc[K];
+    double acc[K], acc2[K];
 #pragma unroll
-    for (int k = 0; k < K; k++) acc[k] = 0.0;
+    for (int k = 0; k < K; k++) acc[k] = acc2[k] = 0.0;
     long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i, acc);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n; i += 2 * stride)
+    {
+        f(i, acc);
+        f(i + stride, acc2);
+    }
+    if (i < n) f(i, acc);
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] += acc2[k];
     block_sum<K>(acc, smem);
     if (threadIdx.x == 0)
     {
