@@ -390,6 +390,13 @@ typedef struct prfdd_krylov_state
 } prfdd_krylov_state;
 
 int prfdd_krylov_reset(prfdd_krylov_state *st, prfdd_stream_t stream);           /* new solve: stopped = 0 */
+/* outer flexible CG as one CUDA graph (loop = conditional WHILE node): the loop test of domain.tpp:683-695 on the device.
+ * state[0] = norms recorded, state[1] = completed search-direction updates; hist[k] = sqrt(*sum) is appended; with has_handle the
+ * graph condition `cond_handle` (cudaGraphConditionalHandle) is set to "continue" exactly as the host loop decides */
+int prfdd_fcg_outer_reset(int *state, prfdd_stream_t stream);
+int prfdd_fcg_outer_check(const double *sum, double *hist, int *state, double tolerance, int use_relative, int max_iterations,
+                          unsigned long long cond_handle, int has_handle, prfdd_stream_t stream);
+int prfdd_fcg_outer_count(int *state, prfdd_stream_t stream);
 /* gamma[0] = sqrt(red[0]); first cycle: r0_norm = gamma[0]; inv_gamma0 = 1/gamma[0]  (tpp:4343-4365) */
 int prfdd_gmres_begin_cycle(prfdd_krylov_state *st, int first_cycle, prfdd_stream_t stream);
 /* column j: H[0..j][j] = hcol, Givens, alpha = sqrt(red[0]), stop tests of tpp:4415-4453 */
@@ -496,6 +503,9 @@ typedef struct prfdd_options
     int verbose;              /* print the reference's "Iter ..." lines on rank 0 */
     int amg_coarsening;       /* -1 library default, 0 PMIS, 1 HMIS (HYPRE coarsen type 10, subdomain.tpp:1853) */
     int amg_precision;        /* 0 FP64 (`Float double`, the reference's setting, AMG/config.hpp:4), 1 FP32 V-cycle (`Float float`) */
+    int device_outer_loop;    /* 1 (default): from the second solve on given buffers the outer flexible CG is ONE CUDA graph whose loop is a
+                               * conditional WHILE node with the convergence test on the device -- no host round trip per iteration
+                               * (domain.tpp:611-725 reads three reductions per iteration on the host); 0: host-driven loop */
 } prfdd_options;
 
 void prfdd_options_default(prfdd_options *opt);

@@ -29,7 +29,7 @@ class Options(C.Structure):
                 ("inner_num_vectors", C.c_int), ("inner_max_iterations", C.c_int), ("num_vcycles", C.c_int),
                 ("cheby_order", C.c_int), ("use_cuda_graph", C.c_int), ("proc_id", C.c_int), ("num_procs", C.c_int),
                 ("nccl_unique_id", C.c_void_p), ("outer_tolerance", C.c_double), ("inner_tolerance", C.c_double),
-                ("outer_max_iterations", C.c_int), ("outer_num_vectors", C.c_int), ("verbose", C.c_int), ("amg_coarsening", C.c_int), ("amg_precision", C.c_int)]
+                ("outer_max_iterations", C.c_int), ("outer_num_vectors", C.c_int), ("verbose", C.c_int), ("amg_coarsening", C.c_int), ("amg_precision", C.c_int), ("device_outer_loop", C.c_int)]
 
 
 def lib():

@@ -94,6 +94,7 @@ void prfdd_options_default(prfdd_options *o)
     o->verbose = 0;
     o->amg_coarsening = -1;
     o->amg_precision = 0;
+    o->device_outer_loop = 1;
 }
 
 int prfdd_solver_create(prfdd_solver **out, const char *directory, const prfdd_options *opt, prfdd_stream_t stream)
@@ -133,6 +134,11 @@ int prfdd_solver_create(prfdd_solver **out, const char *directory, const prfdd_o
         s->domain->tolerance = opt->outer_tolerance;
         s->domain->preconditioner_type = opt->preconditioner_type;
         s->domain->use_preconditioner = opt->use_preconditioner != 0;
+        {
+            static const char *env = getenv("PRFDD_DEVICE_OUTER_LOOP"); // experiment knob: overrides the option
+            const int want = env ? atoi(env) : opt->device_outer_loop;
+            s->domain->device_outer_loop = want != 0 && opt->use_cuda_graph != 0 && (opt->num_procs == 1 || want > 1);
+        }
         if (opt->use_preconditioner)
         {
             int level = N;

@@ -84,6 +84,8 @@ class Domain
 
     void halo_exchange(const memory &nodes);
     void setup_halo();
+    void residual_norm_dev(const memory &r); // the squared norm into scal[2], no host read
+    template <typename PType> bool fcg_device_loop(memory &u, memory &f, PType &subdomain, bool use_relative);
 
   public:
     // Member variables
@@ -113,6 +115,21 @@ class Domain
     bool use_preconditioner = true;
     DType tolerance = (typeid(DType) == typeid(double)) ? 1.0e-07 : 1.0e-04;
     std::vector<double> history;
+    // Outer FCG as ONE CUDA graph (the loop is a conditional WHILE node, its test runs on the device): no host round trip per
+    // iteration.  The first solve on given buffers runs the host-driven loop (it creates every lazily built piece of state, the
+    // preconditioner's own graphs among them); from the second solve on the graph is used.  Same kernels in the same order: the
+    // residual history is identical bit for bit.
+    bool device_outer_loop = false;
+    struct OuterGraph
+    {
+        cudaGraphExec_t exec = nullptr;
+        long long launches_head = 0, launches_body = 0;
+        double bytes_head = 0.0, bytes_body = 0.0;
+    };
+    std::map<std::tuple<void *, void *, const void *, double, int, int>, OuterGraph> outer_graphs; // present with exec == nullptr: warmed, not built yet
+    memory outer_hist, outer_state;
+    double *outer_hist_hst = nullptr;
+    int *outer_state_hst = nullptr;
 
     // Operator
     memory D_hat;
@@ -497,11 +514,129 @@ template <typename DType>
 DType Domain<DType>::residual_norm_sync(const memory &r)
 {
     // domain.tpp:916-931: sqrt( allreduce( sum r * QQt r * mask ) )
+    residual_norm_dev(r);
+    read_scalars(2, 1);
+    return std::sqrt(scal_hst[2]);
+}
+
+template <typename DType>
+void Domain<DType>::residual_norm_dev(const memory &r)
+{
     direct_stiffness_summation(work_dev[1], r);
     dev::check_rc(prfdd_residual_norm(ws, dp(scal) + 2, dp(r), dp(work_dev[1]), dp(dirichlet_mask), num_local_points, st()), "residual_norm");
     prfdd_host::comm_world.allreduce_sum(dp(scal) + 2, 1);
-    read_scalars(2, 1);
-    return std::sqrt(scal_hst[2]);
+}
+
+// Outer FCG as one graph.  Returns false when this call has to take the host-driven loop (first solve on these buffers, timers on).
+// The loop of domain.tpp:621-725 is rotated so that its test sits at the end of the WHILE body:
+//   head:  initialise, |r_0|, z = M r, p = z, FIRST HALF(0), test
+//   body:  SECOND HALF (z = M r+, beta, p, r), FIRST HALF (q = A p, gamma, theta, u, r+, |r+|), test
+// which executes exactly the launches of the host loop up to its `break`.
+template <typename DType>
+template <typename PType>
+bool Domain<DType>::fcg_device_loop(memory &u, memory &f, PType &subdomain, bool use_relative)
+{
+    using namespace prfdd_host;
+    if (!device_outer_loop || timer.enabled || max_iterations < 1) return false;
+    const auto key = std::make_tuple(u.ptr(), f.ptr(), (const void *)&subdomain, (double)tolerance, use_relative ? 1 : 0, max_iterations);
+    auto it = outer_graphs.find(key);
+    if (it == outer_graphs.end())
+    {
+        outer_graphs.emplace(key, OuterGraph()); // warmed by the host-driven solve the caller runs now
+        return false;
+    }
+    const int P = num_local_points;
+    double *sc = dp(scal);
+    memory &u_k = u;
+    if (!outer_hist.is_initialized())
+    {
+        outer_hist = device.malloc<double>(max_iterations + 2);
+        outer_state = device.malloc<int>(2);
+        dev::check(cudaMallocHost((void **)&outer_hist_hst, sizeof(double) * (max_iterations + 2)), "pinned history");
+        dev::check(cudaMallocHost((void **)&outer_state_hst, sizeof(int) * 2), "pinned loop state");
+    }
+    double *hist = outer_hist.template as<double>();
+    int *state = outer_state.template as<int>();
+    OuterGraph &og = it->second;
+    if (!og.exec)
+    {
+        cudaGraph_t g = nullptr;
+        dev::check(cudaGraphCreate(&g, 0), "cudaGraphCreate");
+        cudaGraphConditionalHandle handle;
+        dev::check(cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault), "cudaGraphConditionalHandleCreate");
+        auto first_half = [&](const memory &r_out) {
+            stiffness_matrix(q_k, p_k);
+            dev::check_rc(prfdd_projection_inner_products(ws, sc + 0, dp(z_k), dp(r_k), dp(p_k), dp(q_k), P, st()), "projection_inner_products");
+            comm_world.allreduce_sum(sc + 0, 2);
+            dev::check_rc(prfdd_solution_and_residual_update_dev(dp(u_k), dp(r_out), dp(r_k), dp(p_k), dp(q_k), sc + 0, sc + 1, P, st()), "solution_and_residual_update");
+            residual_norm_dev(r_out);
+            dev::check_rc(prfdd_fcg_outer_check(sc + 2, hist, state, (double)tolerance, use_relative ? 1 : 0, max_iterations, (unsigned long long)handle, 1, st()), "fcg_outer_check");
+        };
+        // head
+        long long l0 = prfdd_launch_count();
+        double b0 = prfdd_algorithmic_bytes();
+        dev::check(cudaStreamBeginCaptureToGraph(st(), g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCaptureToGraph(head)");
+        dev::check_rc(prfdd_fcg_outer_reset(state, st()), "fcg_outer_reset");
+        dev::check_rc(prfdd_initialize_arrays(dp(u_k), dp(r_k), dp(f), P, st()), "initialize_arrays");
+        residual_norm_dev(r_k);
+        dev::check_rc(prfdd_fcg_outer_check(sc + 2, hist, state, (double)tolerance, use_relative ? 1 : 0, max_iterations, 0ull, 0, st()), "fcg_outer_check(r0)");
+        precondition(z_k, r_k, subdomain);
+        p_k.copyFrom(z_k, P * sizeof(DType));
+        first_half(r_kp1);
+        cudaGraph_t same = nullptr;
+        dev::check(cudaStreamEndCapture(st(), &same), "cudaStreamEndCapture(head)");
+        og.launches_head = prfdd_launch_count() - l0;
+        og.bytes_head = prfdd_algorithmic_bytes() - b0;
+        // the WHILE node after every leaf of the head
+        size_t n_nodes = 0;
+        dev::check(cudaGraphGetNodes(g, nullptr, &n_nodes), "cudaGraphGetNodes");
+        std::vector<cudaGraphNode_t> nodes(n_nodes), leaves;
+        dev::check(cudaGraphGetNodes(g, nodes.data(), &n_nodes), "cudaGraphGetNodes");
+        for (auto nd : nodes)
+        {
+            size_t n_dep = 0;
+            dev::check(cudaGraphNodeGetDependentNodes(nd, nullptr, &n_dep), "cudaGraphNodeGetDependentNodes");
+            if (n_dep == 0) leaves.push_back(nd);
+        }
+        cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+        cp.conditional.handle = handle;
+        cp.conditional.type = cudaGraphCondTypeWhile;
+        cp.conditional.size = 1;
+        cudaGraphNode_t cnode;
+        dev::check(cudaGraphAddNode(&cnode, g, leaves.data(), leaves.size(), &cp), "cudaGraphAddNode(conditional)");
+        cudaGraph_t body = cp.conditional.phGraph_out[0];
+        l0 = prfdd_launch_count();
+        b0 = prfdd_algorithmic_bytes();
+        dev::check(cudaStreamBeginCaptureToGraph(st(), body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCaptureToGraph(body)");
+        precondition(z_k, r_kp1, subdomain);
+        dev::check_rc(prfdd_inner_product_flexible(ws, sc + 3, dp(r_k), dp(r_kp1), dp(z_k), P, st()), "inner_product_flexible");
+        comm_world.allreduce_sum(sc + 3, 1);
+        dev::check_rc(prfdd_residual_and_search_update_dev(dp(p_k), dp(r_k), dp(z_k), dp(r_kp1), sc + 3, sc + 0, P, st()), "residual_and_search_update");
+        dev::check_rc(prfdd_fcg_outer_count(state, st()), "fcg_outer_count");
+        first_half(r_kp1);
+        dev::check(cudaStreamEndCapture(st(), &same), "cudaStreamEndCapture(body)");
+        og.launches_body = prfdd_launch_count() - l0;
+        og.bytes_body = prfdd_algorithmic_bytes() - b0;
+        prfdd_launch_count_add(-(og.launches_head + og.launches_body)); // capturing launched nothing
+        prfdd_algorithmic_bytes_add(-(og.bytes_head + og.bytes_body));
+        dev::check(cudaGraphInstantiate(&og.exec, g, 0), "cudaGraphInstantiate(outer FCG)");
+        cudaGraphDestroy(g);
+    }
+    dev::check(cudaGraphLaunch(og.exec, st()), "cudaGraphLaunch(outer FCG)");
+    dev::check(cudaMemcpyAsync(outer_state_hst, state, 2 * sizeof(int), cudaMemcpyDeviceToHost, st()), "loop state");
+    dev::check(cudaMemcpyAsync(outer_hist_hst, hist, (max_iterations + 2) * sizeof(double), cudaMemcpyDeviceToHost, st()), "history");
+    dev::check(cudaStreamSynchronize(st()), "outer FCG graph");
+    const int norms = outer_state_hst[0], updates = outer_state_hst[1];
+    history.assign(outer_hist_hst, outer_hist_hst + norms);
+    num_iterations = updates;
+    const double r0 = history[0], last = history.back();
+    const bool converged = use_relative ? (last / r0 < tolerance) : (last < tolerance);
+    if (!converged && !std::isnan(last) && norms - 1 >= max_iterations) num_iterations = max_iterations; // the host loop's last search update changes neither u nor the history
+    prfdd_launch_count_add(og.launches_head + (long long)updates * og.launches_body);
+    prfdd_algorithmic_bytes_add(og.bytes_head + updates * og.bytes_body);
+    for (int k = 0; k < norms; k++)
+        rstdout("Iter %2d: | residual_norm = %24.16g | relative_residual_norm = %24.16g | \n", k, history[k], history[k] / r0);
+    return true;
 }
 
 template <typename DType>
@@ -531,6 +666,7 @@ template <typename PType>
 void Domain<DType>::flexible_conjugate_gradient(memory &u, memory &f, PType &subdomain, bool use_relative)
 {
     using namespace prfdd_host;
+    if (fcg_device_loop(u, f, subdomain, use_relative)) return;
     const int P = num_local_points;
     // device scalars: [0] gamma  [1] theta  [2] |r|^2  [3] theta_flex
     double *sc = dp(scal);

@@ -1193,6 +1193,16 @@ template <class Body>
 void Subdomain<DType>::run_captured(int type, const memory &u_l, const memory &f_l, Body body)
 {
     using namespace prfdd_host;
+    {
+        // called while the stream is being captured (the outer solve's graph): the body's launches go straight into that graph
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        dev::check(cudaStreamIsCapturing(st(), &cs), "cudaStreamIsCapturing");
+        if (cs == cudaStreamCaptureStatusActive)
+        {
+            body();
+            return;
+        }
+    }
     if (!opt.use_cuda_graph || timer.enabled)
     {
         long long before = prfdd_launch_count();

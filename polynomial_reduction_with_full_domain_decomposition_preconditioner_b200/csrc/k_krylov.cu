@@ -8,6 +8,29 @@ namespace prfdd
 {
 constexpr int MV = PRFDD_KRYLOV_MAXV;
 
+// Outer flexible CG without host round trips (Domain::flexible_conjugate_gradient, domain.tpp:611-725, as one CUDA graph whose loop
+// is a conditional WHILE node): this kernel is the loop test of domain.tpp:683-695.  state[0] = number of residual norms recorded so
+// far, state[1] = number of completed search-direction updates; hist[k] = k-th residual norm; hist[-1..] untouched.  It records
+// sqrt(*sum), decides exactly as the host loop does (same IEEE sqrt and division) and sets the graph's condition.
+__global__ void k_fcg_outer_check(const double *sum, double *hist, int *state, double tolerance, int use_relative, int max_iterations, unsigned long long handle, int has_handle)
+{
+    const double r_norm = sqrt(*sum);
+    const int k = state[0];
+    hist[k] = r_norm;
+    state[0] = k + 1;
+    unsigned int go = 1;
+    if (k >= 1)
+    {
+        // k-th norm = the residual after the first half of iteration k - 1
+        const bool converged = use_relative ? (r_norm / hist[0] < tolerance) : (r_norm < tolerance);
+        if (converged || isnan(r_norm) || k >= max_iterations) go = 0;
+    }
+    if (has_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)handle, go);
+}
+
+__global__ void k_fcg_outer_count(int *state) { state[1] += 1; }
+__global__ void k_fcg_outer_reset(int *state) { state[0] = 0; state[1] = 0; }
+
 __global__ void k_krylov_reset(prfdd_krylov_state *st)
 {
     st->stopped = 0;
@@ -140,6 +163,22 @@ int prfdd_krylov_reset(prfdd_krylov_state *st, prfdd_stream_t stream)
 {
     k_krylov_reset<<<1, 1, 0, S(stream)>>>(st);
     return launched();
+}
+
+int prfdd_fcg_outer_reset(int *state, prfdd_stream_t stream)
+{
+    k_fcg_outer_reset<<<1, 1, 0, S(stream)>>>(state);
+    return launched(0.0);
+}
+int prfdd_fcg_outer_check(const double *sum, double *hist, int *state, double tolerance, int use_relative, int max_iterations, unsigned long long cond_handle, int has_handle, prfdd_stream_t stream)
+{
+    k_fcg_outer_check<<<1, 1, 0, S(stream)>>>(sum, hist, state, tolerance, use_relative, max_iterations, cond_handle, has_handle);
+    return launched(0.0);
+}
+int prfdd_fcg_outer_count(int *state, prfdd_stream_t stream)
+{
+    k_fcg_outer_count<<<1, 1, 0, S(stream)>>>(state);
+    return launched(0.0);
 }
 int prfdd_gmres_begin_cycle(prfdd_krylov_state *st, int first_cycle, prfdd_stream_t stream)
 {

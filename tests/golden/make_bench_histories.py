@@ -32,6 +32,10 @@ CASES = {
     "s4": ((32, 32, 32), 7, 3, 0.0, 4),
     "t2": ((8, 4, 4), 7, 3, 0.0, 2),            # small multi-rank cases for the tests
     "t1": ((4, 4, 4), 7, 3, 0.0, 1),
+    "c4b": ((8, 8, 8), 9, 3, 0.0, 1),           # BASELINE configs[3] degrees (ladder 9/6/3/1) at bench size:  bench.py --degree 9 --reduction 3 --nel-per-gpu 8
+    "c4w2": ((16, 8, 8), 9, 3, 0.0, 2),         # the same two on 2 ranks (bench.py --gpus 2 ... --nel-per-gpu 8): rings at every ladder degree
+    "c5w2": ((16, 8, 8), 15, 7, 0.0, 2),
+    "c5b": ((8, 8, 8), 15, 7, 0.0, 1),          # BASELINE configs[4] degree (ladder 15/8/1):                 bench.py --degree 15 --reduction 7 --nel-per-gpu 8
 }
 
 

@@ -153,3 +153,44 @@ def test_fp32_vcycle_parity(prfdd, tmp_path, dim, nel, N, r, eps):
     e64 = np.linalg.norm(S64.get_array("U") - us[0]) / np.linalg.norm(us[0])
     assert e32 <= 2.0 * e64 + 1e-9
     S.close(); S64.close()
+
+
+@pytest.mark.parametrize("dim,nel,N,r,eps,inner", [(3, 4, 7, 3, 0.0, 1), (2, 8, 7, 3, 0.05, 1), (3, 3, 4, 3, 0.05, 0)])
+def test_outer_fcg_as_one_graph(prfdd, tmp_path, dim, nel, N, r, eps, inner):
+    """prfdd_options.device_outer_loop: from the second solve on the same buffers the outer flexible CG runs as ONE CUDA graph whose
+    loop is a conditional WHILE node (convergence test on the device, no host round trip per iteration).  Same launches in the same
+    order as the host-driven loop: iteration count, residual history and solution must be IDENTICAL to the first (host-driven)
+    solve, bit for bit, and to a solver that never uses the graph."""
+    _need_gpu()
+    d = str(tmp_path)
+    prfdd.mesh_generate_box(d, dim, nel, N, 1, eps, reduction=r)
+    S = prfdd.Solver(d, poly_degree=N, poly_reduction=r, preconditioner_type=inner, outer_tolerance=1e-9, device_outer_loop=1)
+    S.setup_problem(4)
+    nit1, h1 = S.solve(0); u1 = S.get_array("U").copy()          # host-driven loop (warms every lazily built piece of state)
+    l0 = prfdd.lib().prfdd_launch_count()
+    nit2, h2 = S.solve(0); u2 = S.get_array("U").copy()          # builds and runs the graph
+    l1 = prfdd.lib().prfdd_launch_count()
+    nit3, h3 = S.solve(0); u3 = S.get_array("U").copy()          # replays it
+    l2 = prfdd.lib().prfdd_launch_count()
+    assert nit1 == nit2 == nit3 and nit1 >= 2
+    assert np.array_equal(h1, h2) and np.array_equal(h1, h3)
+    assert np.array_equal(u1, u2) and np.array_equal(u1, u3)
+    assert l1 - l0 == l2 - l1 > 0                                 # the launches inside the graph are counted
+    S.close()
+    T = prfdd.Solver(d, poly_degree=N, poly_reduction=r, preconditioner_type=inner, outer_tolerance=1e-9, device_outer_loop=0)
+    T.setup_problem(4)
+    for _ in range(2):
+        nit, h = T.solve(0)
+        assert nit == nit1 and np.array_equal(h, h1) and np.array_equal(T.get_array("U"), u1)
+    # iteration cap: the graph stops where the host loop stops
+    T.close()
+    for loop in (0, 1):
+        Q = prfdd.Solver(d, poly_degree=N, poly_reduction=r, preconditioner_type=inner, outer_tolerance=1e-30, outer_max_iterations=2, device_outer_loop=loop)
+        Q.setup_problem(4)
+        res = [Q.solve(0) for _ in range(2)]
+        assert res[0][0] == res[1][0] == 2 and np.array_equal(res[0][1], res[1][1]) and len(res[1][1]) == 3
+        if loop == 0:
+            cap_hist = res[0][1]
+        else:
+            assert np.array_equal(res[1][1], cap_hist)
+        Q.close()
