@@ -137,7 +137,8 @@ int prfdd_solver_create(prfdd_solver **out, const char *directory, const prfdd_o
         {
             static const char *env = getenv("PRFDD_DEVICE_OUTER_LOOP"); // experiment knob: overrides the option
             const int want = env ? atoi(env) : opt->device_outer_loop;
-            s->domain->device_outer_loop = want != 0 && opt->use_cuda_graph != 0 && (opt->num_procs == 1 || want > 1);
+            // one rank only: with NCCL collectives inside the WHILE body the 2-rank run hung (measured, killed by its timeout)
+            s->domain->device_outer_loop = want != 0 && opt->use_cuda_graph != 0 && opt->num_procs == 1;
         }
         if (opt->use_preconditioner)
         {
