@@ -27,6 +27,7 @@ constexpr int kSpThreads = 256;
 template <int TPR, int RPG, bool UNIT, class VT, class Epi>
 __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr, const int *__restrict__ col, const VT *__restrict__ val, const VT *__restrict__ x, int row_start, int num_rows, int skip_len, Epi epi)
 {
+    pdl_wait();
     constexpr int RPW = 32 / TPR; // rows per warp and pass
     const int lane = threadIdx.x % TPR;
     const int sub = (threadIdx.x & 31) / TPR;
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv(const int *__restrict__ ptr
 template <bool UNIT, class VT, class Epi>
 __global__ void __launch_bounds__(kSpThreads) k_spmv_long(const int *__restrict__ ptr, const int *__restrict__ col, const VT *__restrict__ val, const VT *__restrict__ x, const int *__restrict__ rows, int count, int num_rows, Epi epi)
 {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (kSpThreads / 32) + (threadIdx.x >> 5);
     if (w >= count) return; // whole warps leave together
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv_long(const int *__restrict_
 template <bool UNIT, class VT, class Epi>
 __global__ void __launch_bounds__(256) k_spmv_single(const int *__restrict__ col, const VT *__restrict__ val, const VT *__restrict__ x, int row_start, int num_rows, Epi epi)
 {
+    pdl_wait();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long r = row_start + (long long)blockIdx.x * blockDim.x + threadIdx.x; r < row_start + num_rows; r += stride) epi((int)r, UNIT ? x[col[r]] : val[r] * x[col[r]]);
 }
@@ -144,6 +147,7 @@ static CsrView<float> view(const prfdd_csr_matrix_f32 &A) { return {A.ptr, A.col
 template <int T, int U, class VT, class Epi>
 __global__ void __launch_bounds__(kSpThreads) k_spmv_sell(const int *__restrict__ off, const int *__restrict__ scol, const VT *__restrict__ sval, const int *__restrict__ srow, const VT *__restrict__ x, int num_slices, int num_rows, Epi epi)
 {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (kSpThreads / 32);
     for (int s = blockIdx.x * (kSpThreads / 32) + (threadIdx.x >> 5); s < num_slices; s += nwarps)
@@ -185,6 +189,7 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv_sell(const int *__restrict_
 template <int T, int U, class VT, class Epi>
 __global__ void __launch_bounds__(kSpThreads, 4) k_spmv_sell_small(const int *__restrict__ off, const int *__restrict__ scol, const VT *__restrict__ sval, const int *__restrict__ srow, const VT *__restrict__ x, int num_slices, int num_rows, Epi epi)
 {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (kSpThreads / 32);
     for (int s = blockIdx.x * (kSpThreads / 32) + (threadIdx.x >> 5); s < num_slices; s += nwarps)
@@ -238,6 +243,7 @@ __global__ void __launch_bounds__(kSpThreads, 4) k_spmv_sell_small(const int *__
 template <int T, int U, class VT, class Epi>
 __global__ void __launch_bounds__(kSpThreads) k_spmv_sell_window(const int *__restrict__ off, const int *__restrict__ scol, const VT *__restrict__ sval, const int *__restrict__ srow, const VT *__restrict__ x, int num_slices, int num_rows, Epi epi)
 {
+    pdl_wait();
     constexpr int R = 32 / T;          // rows per slice
     constexpr int SPW = kSpThreads / R; // slices per window of kSpThreads rows
     __shared__ VT ax[kSpThreads];
@@ -287,11 +293,11 @@ static void launch_sell(const CsrView<VT> &A, const VT *x, cudaStream_t st, Epi 
     // twice over and a warp has at most two slices to walk (measured on the c2 hierarchy: level-1 A 47.2 -> 44.5 us, R of level 0
     // 27.4 -> 21.0 us; but 135 k rows x 8 lanes 29.6 -> 35.8 us, 18 k rows x 16 lanes 12.8 -> 43 us)
     if (A.sell_row && A.sell_window == kSpThreads && T <= 2 && A.num_rows >= 2 * 8 * kSpThreads * num_sms() && !no_window)
-        k_spmv_sell_window<T, 4, VT><<<(A.num_rows + kSpThreads - 1) / kSpThreads, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
+        launch_pdl(k_spmv_sell_window<T, 4, VT, Epi>, (A.num_rows + kSpThreads - 1) / kSpThreads, kSpThreads, 0, st, A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
     else if (A.sell_num_slices <= 4 * (kSpThreads / 32) * num_sms() && !no_small) // half a wave of warps (measured: at a full wave the plain kernel is as fast or faster)
-        k_spmv_sell_small<T, 4, VT><<<grid, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
+        launch_pdl(k_spmv_sell_small<T, 4, VT, Epi>, grid, kSpThreads, 0, st, A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
     else
-        k_spmv_sell<T, 4, VT><<<grid, kSpThreads, 0, st>>>(A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
+        launch_pdl(k_spmv_sell<T, 4, VT, Epi>, grid, kSpThreads, 0, st, A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
 }
 
 template <int TPR, bool UNIT, class VT, class Epi>
@@ -302,9 +308,9 @@ static void launch_spmv(const CsrView<VT> &A, const VT *x, int row_start, int nu
     const bool two = TPR >= 4 && (long long)num_rows * TPR >= (1ll << 21);
     const int skip_len = lr ? A.long_row_threshold : 0x7fffffff;
     const int grid = stream_grid((long long)num_rows * TPR / (two ? 2 : 1), kSpThreads, 1, 16);
-    if (two) k_spmv<TPR, 2, UNIT, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
-    else k_spmv<TPR, 1, UNIT, VT><<<grid, kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
-    if (lr) k_spmv_long<UNIT, VT><<<(A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
+    if (two) launch_pdl(k_spmv<TPR, 2, UNIT, VT, Epi>, grid, kSpThreads, 0, st, A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
+    else launch_pdl(k_spmv<TPR, 1, UNIT, VT, Epi>, grid, kSpThreads, 0, st, A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
+    if (lr) launch_pdl(k_spmv_long<UNIT, VT, Epi>, (A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st, A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
 }
 
 // dispatch on the descriptor.  epi_bytes: algorithmic bytes per row of the epilogue's operands
@@ -325,8 +331,8 @@ static int spmv(const CsrView<VT> &A, const VT *x, int row_start, int num_rows, 
     {
         // one entry per row
         if (!x) return -8;
-        if (unit) k_spmv_single<true, VT><<<stream_grid(num_rows, 256, 2, 8), 256, 0, st>>>(A.col, nullptr, x, row_start, num_rows, epi);
-        else k_spmv_single<false, VT><<<stream_grid(num_rows, 256, 2, 8), 256, 0, st>>>(A.col, A.val, x, row_start, num_rows, epi);
+        if (unit) launch_pdl(k_spmv_single<true, VT, Epi>, stream_grid(num_rows, 256, 2, 8), 256, 0, st, A.col, nullptr, x, row_start, num_rows, epi);
+        else launch_pdl(k_spmv_single<false, VT, Epi>, stream_grid(num_rows, 256, 2, 8), 256, 0, st, A.col, A.val, x, row_start, num_rows, epi);
         return launched(bytes);
     }
     if (A.sell_col && x && !unit && row_start == 0 && num_rows == A.num_rows)
@@ -344,7 +350,7 @@ static int spmv(const CsrView<VT> &A, const VT *x, int row_start, int num_rows, 
         if (A.num_long_rows > 0 && A.long_rows)
         {
             // the listed rows are not in the sliced copy (slot row -1): warp per row from the CSR arrays, as after the row kernels
-            k_spmv_long<false, VT><<<(A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st>>>(A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
+            launch_pdl(k_spmv_long<false, VT, Epi>, (A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st, A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
             prfdd_launch_count_add(1);
         }
         return launched(bytes);
@@ -459,6 +465,7 @@ static int t_cheby_step(VT *u, VT *t_out, const CsrView<VT> &A, const VT *t_in, 
 template <class VT>
 __global__ void __launch_bounds__(256, 4) k_dense_t(VT *__restrict__ x, const VT *__restrict__ M, const VT *__restrict__ b, int n)
 {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= n) return; // whole warps leave together
@@ -544,6 +551,7 @@ __global__ void __launch_bounds__(256) k_scatter_assign(double *__restrict__ dst
 // inverse (a handful of rows) and the collapsed coarse levels of the V-cycle (a couple of thousand rows, amg.hpp).
 __global__ void __launch_bounds__(256, 4) k_dense_solve(double *__restrict__ x, const double *__restrict__ Ainv, const double *__restrict__ b, int n)
 {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= n) return; // whole warps leave together
@@ -736,7 +744,7 @@ int prfdd_csrm_cheby_step_f32(float *u, float *t_out, const prfdd_csr_matrix_f32
 int prfdd_dense_solve_f32(float *x, const float *Ainv, const float *b, int n, prfdd_stream_t stream)
 {
     if (n <= 0) return 0;
-    k_dense_t<float><<<(n + 7) / 8, 256, 0, S(stream)>>>(x, Ainv, b, n);
+    launch_pdl(k_dense_t<float>, (n + 7) / 8, 256, 0, S(stream), x, Ainv, b, n);
     return launched(4.0 * n * (double)n + 8.0 * n);
 }
 
@@ -819,7 +827,7 @@ int prfdd_cheby_step(double *u, double *t_out, const int *ptr, const int *col, c
 int prfdd_dense_solve(double *x, const double *Ainv, const double *b, int n, prfdd_stream_t stream)
 {
     if (n <= 0) return 0;
-    k_dense_solve<<<(n + 7) / 8, 256, 0, S(stream)>>>(x, Ainv, b, n);
+    launch_pdl(k_dense_solve, (n + 7) / 8, 256, 0, S(stream), x, Ainv, b, n);
     return launched(8.0 * n * (double)n + 16.0 * n);
 }
 

@@ -23,6 +23,7 @@ constexpr int kRedMaxK = 8;
 template <class F>
 __global__ void __launch_bounds__(kThreads) k_map(long long n, F f)
 {
+    pdl_wait();
     long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
 }
@@ -32,7 +33,7 @@ template <class F>
 static int map(long long n, cudaStream_t st, double bpe, F f)
 {
     if (n <= 0) return 0;
-    k_map<<<stream_grid(n, kThreads, 2, 8), kThreads, 0, st>>>(n, f);
+    launch_pdl(k_map<F>, stream_grid(n, kThreads, 2, 8), kThreads, 0, st, n, f);
     return launched(bpe * (double)n);
 }
 
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(kRedThreads, 4) k_reduce(long long n, F f, dou
 {
     __shared__ double smem[K * (kRedThreads / 32)];
     __shared__ bool is_last;
+    pdl_wait();
     double acc[K], acc2[K];
 #pragma unroll
     for (int k = 0; k < K; k++) acc[k] = acc2[k] = 0.0;
@@ -130,7 +132,7 @@ static int reduce(prfdd_reduce_ws *ws, double *out, int out_stride, long long n,
     if (ws == nullptr) return -2;
     int grid = stream_grid(n > 0 ? n : 1, kRedThreads, 4, 4);
     if (grid > kRedMaxBlocks) grid = kRedMaxBlocks;
-    k_reduce<K><<<grid, kRedThreads, 0, st>>>(n, f, ws->partials, ws->counter, out, out_stride);
+    launch_pdl(k_reduce<K, F>, grid, kRedThreads, 0, st, n, f, ws->partials, ws->counter, out, out_stride);
     return launched(bpe * (double)n);
 }
 } // namespace prfdd
