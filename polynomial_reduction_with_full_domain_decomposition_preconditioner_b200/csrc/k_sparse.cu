@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kSpThreads) k_spmv_sell_window(const int *__re
 template <int T, class VT, class Epi>
 static void launch_sell(const CsrView<VT> &A, const VT *x, cudaStream_t st, Epi epi)
 {
-    static const int waves = getenv("PRFDD_SELL_WAVES") ? atoi(getenv("PRFDD_SELL_WAVES")) : 8;
+    static const int waves = getenv("PRFDD_SELL_WAVES") ? atoi(getenv("PRFDD_SELL_WAVES")) : 32; // CTAs per SM of the grid (measured on c2: 4 -> 15.0 ms, 8 -> 12.63, 16 -> 12.54, 32 -> 12.44, unlimited -> 12.50)
     const int grid = stream_grid(A.sell_num_slices, kSpThreads / 32, 1, waves);
     static const bool no_window = getenv("PRFDD_SELL_NO_WINDOW_KERNEL") != nullptr;
     static const bool no_small = getenv("PRFDD_SELL_NO_SMALL_KERNEL") != nullptr;
