@@ -307,7 +307,8 @@ static void launch_spmv(const CsrView<VT> &A, const VT *x, int row_start, int nu
     // (AMG level 1 of the 16^3 N=7 problem, 27 entries/row: 54.9 -> 49.1 us; profiles/r1_notes.txt)
     const bool two = TPR >= 4 && (long long)num_rows * TPR >= (1ll << 21);
     const int skip_len = lr ? A.long_row_threshold : 0x7fffffff;
-    const int grid = stream_grid((long long)num_rows * TPR / (two ? 2 : 1), kSpThreads, 1, 16);
+    static const int waves = getenv("PRFDD_SPMV_WAVES") ? atoi(getenv("PRFDD_SPMV_WAVES")) : 16; // experiment knob: CTAs per SM of the grid
+    const int grid = stream_grid((long long)num_rows * TPR / (two ? 2 : 1), kSpThreads, 1, waves);
     if (two) launch_pdl(k_spmv<TPR, 2, UNIT, VT, Epi>, grid, kSpThreads, 0, st, A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
     else launch_pdl(k_spmv<TPR, 1, UNIT, VT, Epi>, grid, kSpThreads, 0, st, A.ptr, A.col, A.val, x, row_start, num_rows, skip_len, epi);
     if (lr) launch_pdl(k_spmv_long<UNIT, VT, Epi>, (A.num_long_rows + kSpThreads / 32 - 1) / (kSpThreads / 32), kSpThreads, 0, st, A.ptr, A.col, A.val, x, A.long_rows, A.num_long_rows, num_rows, epi);
