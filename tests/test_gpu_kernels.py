@@ -426,6 +426,47 @@ def test_sliced_copy_gives_the_row_kernels_sums(G, lanes, window):
     assert np.abs(outs[1][1] - (f - A @ x)).max() <= 1e-13 * (np.abs(A) @ np.abs(x)).max()
 
 
+@pytest.mark.parametrize("lanes", [1, 4])
+def test_sliced_copy_with_long_rows_apart(G, lanes):
+    """descriptor contract: rows on the long_rows list are NOT in the sliced copy (slot row -1, stored as empty rows); the sliced kernel
+    leaves them alone and the warp-per-row launch from the CSR arrays finishes them -- same result as the row kernels"""
+    rng = np.random.default_rng(17 + lanes)
+    lib = G.lib
+    lib.prfdd_sell_layout.restype = C.c_longlong
+    nr = 4100; nc = 3000
+    lens = rng.integers(1, 9, nr); long_rows = np.sort(rng.choice(nr, 30, replace=False)).astype(np.int32); lens[long_rows] = rng.integers(60, 200, 30)
+    ptr = np.zeros(nr + 1, np.int32); ptr[1:] = np.cumsum(lens)
+    col = np.concatenate([np.sort(rng.choice(nc, k, replace=False)) for k in lens]).astype(np.int32)
+    val = rng.standard_normal(ptr[-1])
+    x = rng.standard_normal(nc); f = rng.standard_normal(nr)
+    dptr, dcol, dval, dx, df = (G.dev(a) for a in (ptr, col, val, x, f))
+    T = 24
+    D, keep = csr_descriptor(G, ptr, dptr, dcol, dval, lanes)
+    keep_l = G.dev(long_rows)
+    D.long_rows, D.num_long_rows, D.long_row_threshold = keep_l.data_ptr(), len(long_rows), T
+    ref = G.dev(np.full(nr, 5.0))
+    assert lib.prfdd_csrm_residual(G.p(ref), C.byref(D), G.p(dx), G.p(df), G.stream()) == 0
+    # the matrix without its long rows, sliced in row order, long rows marked -1
+    lens2 = lens.copy(); lens2[long_rows] = 0
+    ptr2 = np.zeros(nr + 1, np.int32); ptr2[1:] = np.cumsum(lens2)
+    keep_mask = np.repeat(lens2 > 0, lens)
+    col2, val2 = col[keep_mask], val[keep_mask]
+    R = 32 // lanes; S = (nr + R - 1) // R
+    off = np.zeros(S + 1, np.int32); slot_row = np.zeros(S * R, np.int32)
+    total = lib.prfdd_sell_layout(P(ptr2), C.c_int(nr), C.c_int(lanes), C.c_int(0), P(off), P(slot_row))
+    scol = np.zeros(max(total, 1), np.int32); sval = np.zeros(max(total, 1))
+    assert lib.prfdd_sell_fill(P(ptr2), P(col2), P(val2), C.c_int(nr), C.c_int(lanes), P(off), P(slot_row), P(scol), P(sval)) == 0
+    slot_row[long_rows] = -1
+    Sd = CsrDesc.from_buffer_copy(D)
+    keep2 = [G.dev(off), G.dev(scol), G.dev(sval), G.dev(slot_row)]
+    Sd.sell_off, Sd.sell_col, Sd.sell_val, Sd.sell_row = (k.data_ptr() for k in keep2)
+    Sd.sell_num_slices, Sd.sell_lanes, Sd.sell_window = S, lanes, 0
+    out = G.dev(np.full(nr, 5.0))
+    assert lib.prfdd_csrm_residual(G.p(out), C.byref(Sd), G.p(dx), G.p(df), G.stream()) == 0
+    G.sync()
+    assert np.array_equal(G.host(out), G.host(ref))
+
+
 @pytest.mark.parametrize("tpr", [1, 2, 4, 8])
 def test_csr_unit_values_and_index_map(G, tpr):
     """val == NULL (all stored values 1.0: Q^T of a conforming region) and ptr == NULL (one entry per row: Q) against the CSR product"""
