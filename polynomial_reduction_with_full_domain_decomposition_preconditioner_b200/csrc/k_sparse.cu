@@ -289,12 +289,13 @@ static void launch_sell(const CsrView<VT> &A, const VT *x, cudaStream_t st, Epi 
     const int grid = stream_grid(A.sell_num_slices, kSpThreads / 32, 1, waves);
     static const bool no_window = getenv("PRFDD_SELL_NO_WINDOW_KERNEL") != nullptr;
     static const bool no_small = getenv("PRFDD_SELL_NO_SMALL_KERNEL") != nullptr;
+    static const int small_max = getenv("PRFDD_SELL_SMALL_MAX") ? atoi(getenv("PRFDD_SELL_SMALL_MAX")) : 4 * (kSpThreads / 32) * num_sms();
     // sorted inside windows of kSpThreads rows (prfdd_sell_layout with window_rows = 256): CTA per window when that still fills the chip
     // twice over and a warp has at most two slices to walk (measured on the c2 hierarchy: level-1 A 47.2 -> 44.5 us, R of level 0
     // 27.4 -> 21.0 us; but 135 k rows x 8 lanes 29.6 -> 35.8 us, 18 k rows x 16 lanes 12.8 -> 43 us)
     if (A.sell_row && A.sell_window == kSpThreads && T <= 2 && A.num_rows >= 2 * 8 * kSpThreads * num_sms() && !no_window)
         launch_pdl(k_spmv_sell_window<T, 4, VT, Epi>, (A.num_rows + kSpThreads - 1) / kSpThreads, kSpThreads, 0, st, A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
-    else if (A.sell_num_slices <= 4 * (kSpThreads / 32) * num_sms() && !no_small) // half a wave of warps (measured: at a full wave the plain kernel is as fast or faster)
+    else if (A.sell_num_slices <= small_max && !no_small) // half a wave of warps (measured: at a full wave the plain kernel is as fast or faster)
         launch_pdl(k_spmv_sell_small<T, 4, VT, Epi>, grid, kSpThreads, 0, st, A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
     else
         launch_pdl(k_spmv_sell<T, 4, VT, Epi>, grid, kSpThreads, 0, st, A.sell_off, A.sell_col, A.sell_val, A.sell_row, x, A.sell_num_slices, A.num_rows, epi);
