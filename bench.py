@@ -347,6 +347,7 @@ def main():
     ap.add_argument("--degree", type=int, default=7, help="polynomial degree N (headline: 7); other values are extra records (configs[3], configs[4]), not the headline")
     ap.add_argument("--reduction", type=int, default=3, help="degree reduction per ladder step (headline: 3 -> ladder 7, 4, 1)")
     ap.add_argument("--nel-per-gpu", type=int, default=16, help="elements per side of a rank's block in weak scaling (headline: 16)")
+    ap.add_argument("--device-outer-loop", action="store_true", help="one rank: run the outer solve as one CUDA graph with a device-side loop test (prfdd_options.device_outer_loop)")
     ap.add_argument("--phases", action="store_true", help="add the fenced per-phase table (reference Timer keys) of one extra solve")
     args = ap.parse_args()
     global N_DEG, REDUCTION, NEL_PER_GPU
@@ -400,7 +401,7 @@ def main():
 
     stream = torch.cuda.Stream()
     S = pr.Solver(mesh_dir, stream=stream.cuda_stream, poly_degree=N_DEG, poly_reduction=REDUCTION, use_preconditioner=use_pc,
-                  outer_tolerance=TOL, proc_id=rank, num_procs=world, nccl_unique_id=uid, amg_coarsening=0 if args.coarsening == "pmis" else 1, amg_precision=1 if args.amg_precision == "float" else 0)
+                  outer_tolerance=TOL, proc_id=rank, num_procs=world, nccl_unique_id=uid, amg_coarsening=0 if args.coarsening == "pmis" else 1, amg_precision=1 if args.amg_precision == "float" else 0, device_outer_loop=1 if args.device_outer_loop else 0)
     S.setup_problem(4)
     stream.synchronize()
     setup_s = time.perf_counter() - t_setup0

@@ -503,9 +503,12 @@ typedef struct prfdd_options
     int verbose;              /* print the reference's "Iter ..." lines on rank 0 */
     int amg_coarsening;       /* -1 library default, 0 PMIS, 1 HMIS (HYPRE coarsen type 10, subdomain.tpp:1853) */
     int amg_precision;        /* 0 FP64 (`Float double`, the reference's setting, AMG/config.hpp:4), 1 FP32 V-cycle (`Float float`) */
-    int device_outer_loop;    /* 1 (default): from the second solve on given buffers the outer flexible CG is ONE CUDA graph whose loop is a
+    int device_outer_loop;    /* 1: from the second solve on given buffers the outer flexible CG is ONE CUDA graph whose loop is a
                                * conditional WHILE node with the convergence test on the device -- no host round trip per iteration
-                               * (domain.tpp:611-725 reads three reductions per iteration on the host); 0: host-driven loop */
+                               * (domain.tpp:611-725 reads three reductions per iteration on the host); one rank only.
+                               * 0 (default): host-driven loop, one 8-byte read per iteration.  Off by default because it measures
+                               * the same (12.80 vs 12.84 ms on c2) and Nsight Compute cannot profile kernel nodes of graphs that
+                               * contain conditional nodes */
 } prfdd_options;
 
 void prfdd_options_default(prfdd_options *opt);

@@ -94,7 +94,7 @@ void prfdd_options_default(prfdd_options *o)
     o->verbose = 0;
     o->amg_coarsening = -1;
     o->amg_precision = 0;
-    o->device_outer_loop = 1;
+    o->device_outer_loop = 0;
 }
 
 int prfdd_solver_create(prfdd_solver **out, const char *directory, const prfdd_options *opt, prfdd_stream_t stream)
