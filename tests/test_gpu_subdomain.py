@@ -194,3 +194,25 @@ def test_outer_fcg_as_one_graph(prfdd, tmp_path, dim, nel, N, r, eps, inner):
         else:
             assert np.array_equal(res[1][1], cap_hist)
         Q.close()
+
+
+def test_solve_host_matches_the_device_resident_solve(prfdd, tmp_path):
+    """prfdd_solver_solve_host (right-hand side from and solution to HOST buffers inside the call): identical iterates to the
+    device-resident solve, bit for bit, for page-locked and pageable buffers and both outer drivers"""
+    _need_gpu()
+    import torch
+    d = str(tmp_path)
+    prfdd.mesh_generate_box(d, 3, 4, 7, 1, 0.0, reduction=3)
+    S = prfdd.Solver(d, poly_degree=7, poly_reduction=3, outer_tolerance=1e-9)
+    S.setup_problem(4)
+    f = S.get_array("F")
+    for solver_id in (0, 1):
+        nit0, h0 = S.solve(solver_id)
+        u0 = S.get_array("U").copy()
+        fh = torch.from_numpy(f.copy()).pin_memory(); uh = torch.full_like(fh, 7.0).pin_memory()
+        nit, h = S.solve_host(fh.numpy(), uh.numpy(), solver_id)
+        assert nit == nit0 and np.array_equal(h, h0) and np.array_equal(uh.numpy(), u0)
+        up = np.full_like(f, 5.0)                               # pageable: staged through the solver's pinned buffers
+        nit, h = S.solve_host(f.copy(), up, solver_id)
+        assert nit == nit0 and np.array_equal(up, u0)
+    S.close()
