@@ -23,6 +23,8 @@ One JSON line on stdout (rank 0).
 oracle port -- the OKL kernels as the plain loops OCCA Serial runs, with the @outer loops on all host threads (the OCCA OpenMP
 analogue) -- on the SAME workload as the B200 arm at N = 1 (configs[1] in full).  A step of that arm is ONE outer PCG iteration
 (the metric is per iteration), so that K steps stay within minutes; a single-thread leg of one solve is reported beside it.
+With --gpus N > 1 the line names the B200 arm's workload at that N and times a bounded sample of it: one 16^3 block (1/N of the
+weak-scaled mesh's elements) as a one-process problem (`config.sample_of_workload`); a full-size oracle solve needs up to an hour of set-up.
 """
 import argparse
 import ctypes as C
@@ -179,6 +181,13 @@ def oracle_problem(nel, threads):
     return W, Sd, f, nodes, time.perf_counter() - t0
 
 
+def osub_ladder(N, r):
+    out = [N]
+    while out[-1] > 1:
+        out.append(max(out[-1] - r, 1))
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -222,11 +231,21 @@ def run_reference(args):
     sample = ("3D 16^3 hex box, N=7 (%d nodes), ladder 7/4/1 -- configs[1] in full; a step = ONE outer PCG iteration of the PR-FDD solve to 1e-8 (%d iterations per solve); "
               "%d iterations timed on %d of %d host threads (the faster of the all-threads and single-thread configurations; the oracle's @outer loops run on the threads: "
               "OCCA OpenMP / Serial analogue); set-up (%.0f s) excluded" % (nodes, full_iters, iters, best, cores, setup_s))
+    # the B200 arm's workload at this GPU count (same string as its `config.workload`); the CPU arm times a bounded sample of it: at N = 1
+    # the workload itself, at N > 1 one 16^3 block of it (1/N of the elements of the weak-scaled mesh) solved as a one-rank problem
+    P3, arm_nel = mesh_of(max(args.gpus, 1), args.scaling)
+    workload = ("3D SEM Poisson, %dx%dx%d hex box mesh, N=%d, FP64, PR-FDD preconditioned flexible CG (ladder %s, overlaps 1/1, inner GMRES(4), 1 V-cycle, Chebyshev order 2)"
+                % (tuple(arm_nel) + (N_DEG, "/".join(str(x) for x in osub_ladder(N_DEG, REDUCTION)))))
+    whole = list(arm_nel) == list(nel)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / max(iters, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3D SEM Poisson, 16x16x16 hex box mesh, N=7, FP64, PR-FDD preconditioned flexible CG (ladder 7/4/1, overlaps 1/1, inner GMRES(4), 1 V-cycle, Chebyshev order 2)",
+            "ms_per_step": 1e3 * dt / max(iters, 1), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload,
                        "tolerance": TOL, "global_nodes": nodes, "iterations_per_solve": full_iters, "step": "one outer PCG iteration (bounded sample of the solve)",
-                       "partition": "1 process (the N-rank composite problems of the B200 arm at N > 1 are not simulated on the CPU: this arm is the N = 1 workload at every N)",
+                       "sample_of_workload": "the workload in full (16^3 elements, one process)" if whole else
+                                             "one 16x16x16 block of the %dx%dx%d mesh (1/%d of its elements) solved as a one-process problem with all host threads: a full-size oracle solve takes "
+                                             "up to an hour of set-up (tests/golden/bench_histories.json), and the N-rank composite problems are not simulated on the CPU"
+                                             % (tuple(arm_nel) + (int(np.prod(arm_nel)) // int(np.prod(nel)),)),
+                       "partition": "1 process",
                        "setup_s": setup_s, "host_threads_available": cores},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": best, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
